@@ -1,0 +1,96 @@
+/* yart_oracle.h -- C entry points of the CPU ORACLE.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement (f64, no FMA contraction) of the
+ * reference's hot path, used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs as the checker and the timed CPU baseline.  The product
+ * (yet-another-raytracer_b200/) never links, imports or calls it.
+ *
+ * PARITY UNPINNED: the reference is nightly Rust + crates.io and cannot be built in this
+ * environment (no cargo/rustc, no network), and its own tests hold no golden vector for this
+ * path.  The oracle is pinned instead against (i) brute-force
+ * all-triangle closest hits, (ii) the known answers of SURVEY.md Appendix D and the
+ * 4-triangle fixture of qbvh.rs:1168-1246, (iii) the reference's 13 semantic unit tests,
+ * restated in tests/.
+ *
+ * It consumes the same plain-C scene description as the product (include/yart.h) so both
+ * see bit-identical inputs.
+ */
+#ifndef YART_ORACLE_H
+#define YART_ORACLE_H
+
+#include "../include/yart.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_scene orc_scene;
+
+const char* orc_last_error(void);
+
+/* world + lights + per-mesh L4QBVH::new (qbvh.rs:251-361) */
+int orc_scene_create(const yart_scene_desc* desc, orc_scene** out);
+void orc_scene_free(orc_scene* s);
+
+typedef struct orc_qbvh_info {
+  uint32_t n_nodes, n_leaves, n_tris, max_stack_seen;
+  uint32_t leaves_by_count[5]; /* [1..4] */
+  uint32_t empty_children;
+  double bbox_min[3], bbox_max[3];
+} orc_qbvh_info;
+int orc_qbvh_info_get(const orc_scene* s, uint32_t mesh, orc_qbvh_info* out);
+/* node i: 24 doubles (min x[4] y[4] z[4], max x[4] y[4] z[4]), 4 child ids, 3 axes */
+int orc_qbvh_node(const orc_scene* s, uint32_t mesh, uint32_t i, double* boxes24,
+                  uint32_t* children4, uint32_t* axes3);
+/* tree-order position -> original triangle index */
+int orc_qbvh_tri_order(const orc_scene* s, uint32_t mesh, uint32_t* orig_index_out);
+
+typedef struct orc_counters {
+  uint64_t rays, node_visits, leaf_visits, tri_tests, max_stack;
+} orc_counters;
+
+/* L4QBVH::hit (qbvh.rs:381-543) / HittableList::hit (hittable.rs:66-79); same contract as
+ * yart_closest_hit.  n_threads <= 1 runs single-threaded. */
+int orc_closest_hit(const orc_scene* s, uint32_t target, const yart_ray* rays, uint64_t n,
+                    double t_min, double t_max, uint32_t order, yart_hit* hits,
+                    orc_counters* counters, int n_threads);
+/* every triangle of the mesh tested with Triangle::hit arithmetic (triangle.rs:48-79);
+ * smallest t wins, ties -> n_ties>1 and prim_id = lowest original index */
+int orc_brute_force_hit(const orc_scene* s, uint32_t mesh, const yart_ray* rays, uint64_t n,
+                        double t_min, double t_max, yart_hit* hits, uint32_t* n_ties);
+/* all original triangle ids whose t equals the brute-force minimum for one ray */
+int orc_tie_set(const orc_scene* s, uint32_t mesh, const yart_ray* ray, double t_min,
+                double t_max, uint32_t* ids, uint32_t cap, uint32_t* n_out);
+
+/* render() sample loop (main.rs:590-718), 8x8 tiles on n_threads workers */
+int orc_render(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
+               double* film_xyz, yart_stats* stats, int n_threads);
+int orc_film_finalize(const double* film_xyz, uint32_t width, uint32_t height, uint32_t spp,
+                      uint8_t* rgba8);
+int orc_camera_rays(const yart_camera* cam, const yart_render_opts* opts, yart_ray* rays,
+                    double* wavelength, double* time);
+/* all world rays (every bounce) of the samples in opts, up to cap; for the path-ray sweep */
+int orc_dump_path_rays(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
+                       yart_ray* rays, uint64_t cap, uint64_t* n_out);
+/* one sample's value before sanitising + its ray count (debugging parity) */
+int orc_sample(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
+               uint32_t pixel, uint32_t sample, double* xyz3, uint32_t* n_rays);
+
+/* small pure functions mirrored from the reference's unit tests */
+void orc_sanitize_sample_xyz(const double* in3, double* out3);      /* main.rs:448-459 */
+uint8_t orc_clamp_display_channel(double c);                         /* main.rs:461-463 */
+void orc_gamma_corrected(const double* rgb3, double* out3);          /* color.rs:92-107 */
+double orc_rgb_reflect(const double* rgb3, double wavelength);       /* color.rs:160-164 */
+void orc_xyz_from_wavelength(double wavelength, double* xyz3);       /* color.rs:216-227 */
+void orc_xyz_into_rgb(const double* xyz3, double* rgb3);             /* color.rs:174-214 */
+double orc_sellmeier_index(const yart_material* m, double wavelength); /* material.rs:247-253 */
+int orc_push_hit_children(uint32_t* stack, uint32_t* cursor, const uint32_t* children4,
+                          const uint32_t* order4, const uint8_t* hits4); /* qbvh.rs:18-31 */
+void orc_philox4x32_10(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4);
+void orc_uniform2(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t slot,
+                  double* u2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

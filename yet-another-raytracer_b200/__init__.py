@@ -1,0 +1,333 @@
+"""yet-another-raytracer_b200 -- host-side mirror of the reference's interface over the C ABI.
+
+The product is `libyart_b200.so` (hand-written sm_100a CUDA + a C++ host front end, built by
+build.py from csrc/).  This module is the thin ctypes binding used by the tests, bench.py and
+the CLI; names follow the reference (TriangleMesh.from_obj, L4QBVH, build_scene_preset,
+resolve_dimensions, render ...).  There is no CPU fallback: if the shared library is missing
+every entry point raises, and compute calls fail with YART_ERR_CUDA when no B200 is present.
+
+The package name has a hyphen, so import it with
+    importlib.import_module("yet-another-raytracer_b200")
+"""
+import ctypes as C
+import gzip
+import os
+import shutil
+from pathlib import Path
+
+import numpy as np
+
+from . import _abi as abi
+from ._abi import (FLAG_COUNT_VISITS, FLAG_DEVICE_PTRS, HIT_DTYPE, MISS, ORDER_NEAR, ORDER_REFERENCE, RAY_DTYPE,
+                   TARGET_WORLD, make_rays)
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "libyart_b200.so"
+
+SCENE_NAMES = ["random-scene", "two-spheres", "two-perlin-spheres", "earth", "simple-light", "cornell-box",
+               "cornell-box-smoke", "next-week-final", "teapot", "bunny", "three-spheres", "sycee", "david"]
+
+
+class YartError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("yart error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Load libyart_b200.so (built in-tree by build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError("%s is missing: run `python %s` (or __graft_entry__.build()) first; "
+                          "there is no Python/CPU fallback" % (LIB_PATH, PKG_DIR / "build.py"))
+    lib = C.CDLL(str(LIB_PATH))
+    P = C.POINTER
+    vp, u32, u64, f64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_double, C.c_int
+    sig = {
+        "yart_version": (C.c_char_p, []),
+        "yart_last_error_global": (C.c_char_p, []),
+        "yart_obj_load": (i32, [C.c_char_p, P(vp)]),
+        "yart_obj_free": (None, [vp]),
+        "yart_obj_trimesh": (i32, [vp, P(abi.Trimesh)]),
+        "yart_qbvh_build": (i32, [P(abi.Trimesh), P(vp)]),
+        "yart_qbvh_free": (None, [vp]),
+        "yart_qbvh_get_info": (i32, [vp, P(abi.QbvhInfo)]),
+        "yart_qbvh_nodes": (vp, [vp]),
+        "yart_qbvh_tris": (vp, [vp]),
+        "yart_preset_build": (i32, [C.c_char_p, C.c_char_p, u64, P(vp)]),
+        "yart_preset_free": (None, [vp]),
+        "yart_preset_scene": (P(abi.SceneDesc), [vp]),
+        "yart_preset_get_info": (i32, [vp, P(abi.PresetInfo)]),
+        "yart_preset_count": (i32, []),
+        "yart_preset_name": (C.c_char_p, [i32]),
+        "yart_resolve_dimensions": (None, [u32, u32, u32, u32, P(u32), P(u32)]),
+        "yart_preset_camera": (i32, [vp, u32, u32, f64, f64, P(abi.Camera)]),
+        "yart_device_count": (i32, []),
+        "yart_ctx_create": (i32, [i32, P(vp)]),
+        "yart_ctx_destroy": (None, [vp]),
+        "yart_last_error": (C.c_char_p, [vp]),
+        "yart_ctx_set_stream": (i32, [vp, vp]),
+        "yart_ctx_synchronize": (i32, [vp]),
+        "yart_ctx_set_scene": (i32, [vp, P(abi.SceneDesc)]),
+        "yart_closest_hit": (i32, [vp, u32, vp, u64, f64, f64, u32, u32, vp, P(abi.Stats)]),
+        "yart_render": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, P(abi.Stats)]),
+        "yart_film_finalize": (i32, [vp, vp, u32, u32, u32, u32, vp]),
+        "yart_generate_camera_rays": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "yart_version", "yart_last_error_global", "yart_obj_load", "yart_obj_free", "yart_obj_trimesh", "yart_qbvh_build",
+    "yart_qbvh_free", "yart_qbvh_get_info", "yart_qbvh_nodes", "yart_qbvh_tris", "yart_preset_build",
+    "yart_preset_free", "yart_preset_scene", "yart_preset_get_info", "yart_preset_count", "yart_preset_name",
+    "yart_resolve_dimensions", "yart_preset_camera", "yart_device_count", "yart_ctx_create", "yart_ctx_destroy",
+    "yart_last_error", "yart_ctx_set_stream", "yart_ctx_synchronize", "yart_ctx_set_scene", "yart_closest_hit",
+    "yart_render", "yart_film_finalize", "yart_generate_camera_rays",
+]
+
+
+def _check_global(rc):
+    if rc != 0:
+        raise YartError(rc, load_library().yart_last_error_global().decode())
+
+
+def assets_dir():
+    """Directory with cube.obj / david.obj / sycee.obj / earthmap_1024x512.rgb8.
+
+    The repository ships them gzip-compressed under assets/ (they are the reference's own
+    input files; /root/reference does not exist on the GPU box); they are unpacked on first use.
+    """
+    src = REPO_ROOT / "assets"
+    dst = src / "_unpacked"
+    dst.mkdir(exist_ok=True)
+    for gz in sorted(src.glob("*.gz")):
+        out = dst / gz.name[:-3]
+        if not out.exists() or out.stat().st_mtime < gz.stat().st_mtime:
+            tmp = out.with_suffix(out.suffix + ".tmp%d" % os.getpid())
+            with gzip.open(gz, "rb") as fi, open(tmp, "wb") as fo:
+                shutil.copyfileobj(fi, fo)
+            os.replace(tmp, out)
+    return str(dst)
+
+
+class TriangleMesh:
+    """`TriangleMesh::from_obj` (reference triangle.rs:110-175) up to the triangle list."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.trimesh = abi.Trimesh()
+        _check_global(load_library().yart_obj_trimesh(self._h, C.byref(self.trimesh)))
+
+    @classmethod
+    def from_obj(cls, path):
+        h = C.c_void_p()
+        _check_global(load_library().yart_obj_load(str(path).encode(), C.byref(h)))
+        return cls(h)
+
+    @property
+    def n_tris(self):
+        return int(self.trimesh.n_tris)
+
+    def positions(self):
+        return np.ctypeslib.as_array(self.trimesh.positions, shape=(self.n_tris, 3, 3)).copy()
+
+    def normals(self):
+        return np.ctypeslib.as_array(self.trimesh.normals, shape=(self.n_tris, 3, 3)).copy()
+
+    def uvs(self):
+        return np.ctypeslib.as_array(self.trimesh.uvs, shape=(self.n_tris, 3, 2)).copy()
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.yart_obj_free(self._h)
+            self._h = None
+
+
+class L4QBVH:
+    """`L4QBVH::new` (reference qbvh.rs:251-361), flattened into the device layout."""
+
+    def __init__(self, trimesh, keepalive=None):
+        self._keep = keepalive
+        self._h = C.c_void_p()
+        _check_global(load_library().yart_qbvh_build(C.byref(trimesh), C.byref(self._h)))
+        self.info = abi.QbvhInfo()
+        _check_global(_lib.yart_qbvh_get_info(self._h, C.byref(self.info)))
+
+    @classmethod
+    def from_mesh(cls, mesh):
+        return cls(mesh.trimesh, keepalive=mesh)
+
+    def nodes(self):
+        n = self.info.n_nodes
+        buf = (C.c_char * (n * 128)).from_address(_lib.yart_qbvh_nodes(self._h))
+        return np.frombuffer(buf, dtype=abi.NODE_DTYPE, count=n).copy()
+
+    def tris(self):
+        n = self.info.n_tris
+        buf = (C.c_char * (n * 48)).from_address(_lib.yart_qbvh_tris(self._h))
+        return np.frombuffer(buf, dtype=abi.TRI_DTYPE, count=n).copy()
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.yart_qbvh_free(self._h)
+            self._h = None
+
+
+def resolve_dimensions(default_width, default_height, width_override=None, height_override=None):
+    """`resolve_dimensions` (reference main.rs:166-186)."""
+    w, h = C.c_uint32(), C.c_uint32()
+    load_library().yart_resolve_dimensions(default_width, default_height, width_override or 0, height_override or 0,
+                                           C.byref(w), C.byref(h))
+    return int(w.value), int(h.value)
+
+
+class ScenePreset:
+    """`build_scene_preset` (reference main.rs:211-432): world, sampling lights, camera, defaults."""
+
+    def __init__(self, name, assets=None, seed=1):
+        self.name = name
+        self._h = C.c_void_p()
+        _check_global(load_library().yart_preset_build(name.encode(), (assets or assets_dir()).encode(), seed,
+                                                       C.byref(self._h)))
+        self.info = abi.PresetInfo()
+        _check_global(_lib.yart_preset_get_info(self._h, C.byref(self.info)))
+        self.desc = _lib.yart_preset_scene(self._h)  # POINTER(SceneDesc), borrowed
+
+    def camera(self, width, height, vfov=None, aperture=None):
+        cam = abi.Camera()
+        _check_global(_lib.yart_preset_camera(self._h, width, height, -1.0 if vfov is None else vfov,
+                                              -1.0 if aperture is None else aperture, C.byref(cam)))
+        return cam
+
+    def resolve_render_options(self, output=None, width=None, height=None, samples=None, max_depth=None,
+                               workers=None, vfov=None, aperture=None):
+        """`resolve_render_options` (reference main.rs:188-209)."""
+        w, h = resolve_dimensions(self.info.width, self.info.height, width, height)
+        return {
+            "output_path": output or os.path.join("output", self.info.output_filename.decode()),
+            "width": w, "height": h,
+            "samples_per_pixel": samples or self.info.samples_per_pixel,
+            "max_depth": max_depth or self.info.max_depth,
+            "workers": workers or self.info.workers,
+            "vfov": self.info.vfov if vfov is None else vfov,
+            "aperture": self.info.aperture if aperture is None else aperture,
+        }
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.yart_preset_free(self._h)
+            self._h = None
+
+
+def device_count():
+    return int(load_library().yart_device_count())
+
+
+class Context:
+    """One GPU.  Not thread-safe; N GPUs = N contexts (one process per GPU in bench.py)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check_global(load_library().yart_ctx_create(device, C.byref(self._h)))
+        self.device = device
+        self._scene_keep = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise YartError(rc, _lib.yart_last_error(self._h).decode())
+
+    def set_scene(self, scene):
+        """scene: a ScenePreset or a ctypes pointer to SceneDesc."""
+        desc = scene.desc if isinstance(scene, ScenePreset) else scene
+        self._scene_keep = scene
+        self._check(_lib.yart_ctx_set_scene(self._h, desc))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(_lib.yart_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._check(_lib.yart_ctx_synchronize(self._h))
+
+    def closest_hit(self, rays, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"), order=ORDER_REFERENCE,
+                    count_visits=False):
+        """Batched `Hittable::hit` (reference hittable.rs:24) with host buffers."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        st = abi.Stats()
+        flags = FLAG_COUNT_VISITS if count_visits else 0
+        self._check(_lib.yart_closest_hit(self._h, target, rays.ctypes.data, rays.shape[0], t_min, t_max, order, flags,
+                                          hits.ctypes.data, C.byref(st)))
+        return hits, st
+
+    def closest_hit_device(self, rays_ptr, n, hits_ptr, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"),
+                           order=ORDER_REFERENCE, count_visits=False):
+        """Same with device pointers (e.g. torch tensors' data_ptr()) -- nothing crosses PCIe."""
+        st = abi.Stats()
+        flags = FLAG_DEVICE_PTRS | (FLAG_COUNT_VISITS if count_visits else 0)
+        self._check(_lib.yart_closest_hit(self._h, target, C.c_void_p(rays_ptr), n, t_min, t_max, order, flags,
+                                          C.c_void_p(hits_ptr), C.byref(st)))
+        return st
+
+    def _opts(self, width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp, flags):
+        o = abi.RenderOpts()
+        o.width, o.height = width, height
+        o.sample_begin, o.sample_end = sample_begin, sample_end
+        o.max_depth, o.order, o.batch_spp, o.flags, o.seed = max_depth, order, batch_spp, flags, seed
+        return o
+
+    def render(self, camera, width, height, sample_begin, sample_end, max_depth=50, seed=1, order=ORDER_NEAR,
+               batch_spp=0, film=None):
+        """Batched sample loop of `render` (reference main.rs:650-708).  Returns (film, stats);
+        film is the (H, W, 3) f64 sum of sanitised XYZ samples (continued if `film` is given)."""
+        if film is None:
+            film = np.zeros((height, width, 3), dtype=np.float64)
+        assert film.dtype == np.float64 and film.shape == (height, width, 3) and film.flags.c_contiguous
+        st = abi.Stats()
+        o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp, 0)
+        self._check(_lib.yart_render(self._h, C.byref(camera), C.byref(o), film.ctypes.data, C.byref(st)))
+        return film, st
+
+    def render_device(self, camera, width, height, sample_begin, sample_end, film_ptr, max_depth=50, seed=1,
+                      order=ORDER_NEAR, batch_spp=0):
+        st = abi.Stats()
+        o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp, FLAG_DEVICE_PTRS)
+        self._check(_lib.yart_render(self._h, C.byref(camera), C.byref(o), C.c_void_p(film_ptr), C.byref(st)))
+        return st
+
+    def film_finalize(self, film, spp):
+        """Per-pixel finalisation (reference main.rs:710-718) -> (H, W, 4) u8."""
+        film = np.ascontiguousarray(film, dtype=np.float64)
+        h, w = film.shape[:2]
+        rgba = np.empty((h, w, 4), dtype=np.uint8)
+        self._check(_lib.yart_film_finalize(self._h, film.ctypes.data, w, h, spp, 0, rgba.ctypes.data))
+        return rgba
+
+    def camera_rays(self, camera, width, height, sample_begin, sample_end, seed=1):
+        n = width * height * (sample_end - sample_begin)
+        rays = np.empty(n, dtype=RAY_DTYPE)
+        wl = np.empty(n, dtype=np.float64)
+        tm = np.empty(n, dtype=np.float64)
+        o = self._opts(width, height, sample_begin, sample_end, 1, seed, ORDER_REFERENCE, 0, 0)
+        self._check(_lib.yart_generate_camera_rays(self._h, C.byref(camera), C.byref(o), rays.ctypes.data,
+                                                   wl.ctypes.data, tm.ctypes.data))
+        return rays, wl, tm
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.yart_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()

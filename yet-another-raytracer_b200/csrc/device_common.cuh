@@ -1,0 +1,149 @@
+// device_common.cuh -- device-side vocabulary: f64 vector math in the reference's operation
+// order, Philox4x32-10, spectral tables, and the scene structures as they sit in HBM.
+//
+// Everything here is compiled with -fmad=false: the reference is plain f64 Rust without FMA
+// contraction, and bit-exact closest-hit parity depends on evaluating (a*b + c*d) the same way.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/yart.h"
+#include "../../include/yart_rng.h"
+
+namespace yart {
+
+#define YART_DEV __device__ __forceinline__
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kF64Eps = 2.220446049250313e-16; // f64::EPSILON
+constexpr double kF64Max = 1.7976931348623157e308;
+
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// ---------------------------------------------------------------------------------------------
+// Vec3 (reference vec3.rs) -- same association order as the Rust operators
+// ---------------------------------------------------------------------------------------------
+struct D3 {
+  double x, y, z;
+};
+YART_DEV D3 d3(double x, double y, double z) { return D3{x, y, z}; }
+YART_DEV D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+YART_DEV D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+YART_DEV D3 operator-(D3 a) { return d3(-a.x, -a.y, -a.z); }
+YART_DEV D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+YART_DEV D3 operator*(double s, D3 a) { return d3(s * a.x, s * a.y, s * a.z); }
+YART_DEV D3 vdiv(D3 a, double s) { // Div<f64> (vec3.rs:113-123)
+  if (s == 0.0) return d3(kF64Max, kF64Max, kF64Max);
+  return d3(a.x / s, a.y / s, a.z / s);
+}
+YART_DEV double dot(D3 a, D3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+YART_DEV D3 cross(D3 a, D3 b) {
+  return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+YART_DEV double length_squared(D3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+YART_DEV double length(D3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+YART_DEV D3 unit_vector(D3 a) {
+  double l = length(a);
+  return d3(a.x / l, a.y / l, a.z / l);
+}
+YART_DEV double comp(D3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 and the draw contract (include/yart_rng.h)
+// ---------------------------------------------------------------------------------------------
+struct Rng {
+  uint32_t k0, k1, pixel, sample;
+};
+YART_DEV Rng make_rng(uint64_t seed, uint32_t pixel, uint32_t sample) {
+  Rng r;
+  r.k0 = (uint32_t)(seed & 0xffffffffu);
+  r.k1 = (uint32_t)(seed >> 32);
+  r.pixel = pixel;
+  r.sample = sample;
+  return r;
+}
+YART_DEV void rng_draw(const Rng& r, uint32_t bounce, uint32_t slot, double& u0, double& u1) {
+  uint32_t c0 = r.pixel, c1 = r.sample, c2 = bounce, c3 = slot, k0 = r.k0, k1 = r.k1;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t h0 = __umulhi(YART_PHILOX_M0, c0), l0 = YART_PHILOX_M0 * c0;
+    const uint32_t h1 = __umulhi(YART_PHILOX_M1, c2), l1 = YART_PHILOX_M1 * c2;
+    const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += YART_PHILOX_W0;
+    k1 += YART_PHILOX_W1;
+  }
+  const uint64_t a = (uint64_t)c0 | ((uint64_t)c1 << 32);
+  const uint64_t b = (uint64_t)c2 | ((uint64_t)c3 << 32);
+  u0 = (double)(a >> 11) * (1.0 / 9007199254740992.0);
+  u1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// random_in_unit_sphere (material.rs:308-324) on the contract's slots
+YART_DEV D3 random_in_unit_sphere(const Rng& rng, uint32_t bounce) {
+  for (uint32_t i = 0; i < YART_MAX_REJECT; ++i) {
+    double a, b, c, unused;
+    rng_draw(rng, bounce, YART_SLOT_SPHERE + 2 * i, a, b);
+    rng_draw(rng, bounce, YART_SLOT_SPHERE + 2 * i + 1, c, unused);
+    D3 p = d3(-1.0 + 2.0 * a, -1.0 + 2.0 * b, -1.0 + 2.0 * c);
+    if (length_squared(p) >= 1.0) continue;
+    return p;
+  }
+  return d3(0.0, 0.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scene in HBM
+// ---------------------------------------------------------------------------------------------
+struct DevMesh {
+  const float4* nodes;  // 8 float4 per node (host_common.h FlatNode)
+  const float4* tris;   // 3 float4 per triangle, tree order (FlatTri)
+  const double* shade;  // 12 doubles per triangle (FlatTriShade: 9 normals + 6 float uvs)
+  uint32_t root;
+  uint32_t max_stack;
+};
+
+// A flat 4-wide tree over the members of a BVHNode group (spheres / boxes).  Same 128-byte node
+// as the triangle QBVH; leaves hold up to 4 member indices.
+struct DevGroup {
+  const float4* nodes;
+  const yart_object* members;  // in tree order
+  const uint32_t* member_orig; // tree position -> index in yart_group.members
+  uint32_t root;      // 0xFFFFFFFF when the group is tiny and scanned linearly
+  uint32_t n_members;
+};
+
+struct DevImage {
+  const uint8_t* rgb8;
+  uint32_t width, height;
+};
+
+struct DevScene {
+  const yart_object* objects;
+  const yart_object* lights;
+  const DevMesh* meshes;
+  const DevGroup* groups;
+  const yart_material* materials;
+  const yart_texture* textures;
+  const yart_perlin* perlins;
+  const DevImage* images;
+  const double* cie;   // [3][471]
+  const double* smits; // [7][36]
+  uint32_t n_objects, n_lights;
+  double background[3];
+};
+
+// What a closest-hit query leaves behind for the shade stage (32 bytes).
+struct alignas(16) DevHit {
+  double t;      // +inf on a miss
+  double bu, bv; // barycentric weights of v1, v2 (mesh / loose triangle hits)
+  uint32_t obj;  // world object index, YART_MISS on a miss
+  uint32_t prim; // mesh: triangle position in tree order; box: side; group: member
+};
+
+struct DevCamera { // Camera (camera.rs:11-23), derived on the host by Camera::new
+  double llc[3], horizontal[3], vertical[3], origin[3], u[3], v[3];
+  double lens_radius, time0, time1;
+};
+
+} // namespace yart

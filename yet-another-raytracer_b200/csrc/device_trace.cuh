@@ -1,0 +1,450 @@
+// device_trace.cuh -- closest-hit: the persistent-thread QBVH traversal kernel and the analytic
+// primitives around it.
+//
+// One lane = one ray.  A lane is a small state machine that walks the world's object list in
+// order (HittableList::hit, reference hittable.rs:66-79): analytic objects are intersected in
+// place, a TriangleMesh object switches the lane into QBVH traversal (L4QBVH::hit,
+// qbvh.rs:381-543) with the ray moved into the instance's space (Translate / RotateY,
+// hittable.rs:136-152, 217-251).  Lanes that run out of work fetch the next ray from a global
+// counter (warp-aggregated), so a warp stays full while rays of very different cost retire.
+// The traversal stack lives in shared memory, one column per lane (no bank conflicts).
+#pragma once
+#include "device_common.cuh"
+
+namespace yart {
+
+constexpr int kTraceThreads = 128;
+constexpr uint32_t kSentinel = 0x7FFFFFFFu; // "no traversal in progress" (never a valid node id)
+
+// ORDER_TABLE (qbvh.rs:14-16) packed 16 bits per entry
+constexpr unsigned long long kOrderLo = 0x1032102301320123ULL; // entries 0..3
+constexpr unsigned long long kOrderHi = 0x3210231032012301ULL; // entries 4..7
+
+// ---------------------------------------------------------------------------------------------
+// analytic primitives, t-only (the shade stage rebuilds the full HitRecord from t)
+// ---------------------------------------------------------------------------------------------
+// StillSphere::hit / MovingSphere::hit root selection (sphere.rs:48-66, 156-173)
+YART_DEV bool sphere_t(D3 center, double radius, D3 ro, D3 rd, double t_min, double t_max, double& t) {
+  D3 oc = ro - center;
+  double a = length_squared(rd);
+  double half_b = dot(oc, rd);
+  double c = length_squared(oc) - radius * radius;
+  double disc = half_b * half_b - a * c;
+  if (disc < 0.0) return false;
+  t = (0.0 - half_b - sqrt(disc)) / a;
+  if (t < t_min || t_max < t) {
+    t = (0.0 - half_b + sqrt(disc)) / a;
+    if (t < t_min || t_max < t) return false;
+  }
+  return true;
+}
+YART_DEV D3 moving_center(const yart_object& o, double time) { // sphere.rs:149-152
+  D3 c0 = d3(o.p[0], o.p[1], o.p[2]), c1 = d3(o.p[3], o.p[4], o.p[5]);
+  return c0 + ((time - o.p[6]) / (o.p[7] - o.p[6])) * (c1 - c0);
+}
+// XYRect/XZRect/YZRect::hit (aarect.rs:41-57, 111-127, 206-222); kaxis = constant axis
+YART_DEV bool rect_t(int kaxis, double a0, double a1, double b0, double b1, double k, D3 ro, D3 rd, double t_min,
+                     double t_max, double& t) {
+  const int aa = (kaxis == 0) ? 1 : 0;
+  const int ba = (kaxis == 2) ? 1 : 2;
+  t = (k - comp(ro, kaxis)) / comp(rd, kaxis);
+  if (t < t_min || t > t_max) return false;
+  double a = comp(ro, aa) + t * comp(rd, aa);
+  double b = comp(ro, ba) + t * comp(rd, ba);
+  if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+  return true;
+}
+YART_DEV int rect_axis(uint32_t kind) { return kind == YART_OBJ_XY_RECT ? 2 : (kind == YART_OBJ_XZ_RECT ? 1 : 0); }
+// the six sides of BoxEntity::new in order (box_entity.rs:28-45)
+YART_DEV void box_side(const double* p, int i, int& axis, double& a0, double& a1, double& b0, double& b1, double& k) {
+  const double x0 = p[0], y0 = p[1], z0 = p[2], x1 = p[3], y1 = p[4], z1 = p[5];
+  if (i < 2) { axis = 2; a0 = x0; a1 = x1; b0 = y0; b1 = y1; k = (i == 0) ? z0 : z1; }
+  else if (i < 4) { axis = 1; a0 = x0; a1 = x1; b0 = z0; b1 = z1; k = (i == 2) ? y0 : y1; }
+  else { axis = 0; a0 = y0; a1 = y1; b0 = z0; b1 = z1; k = (i == 4) ? x0 : x1; }
+}
+YART_DEV bool box_t(const double* p, D3 ro, D3 rd, double t_min, double t_max, double& t, uint32_t& side) {
+  bool any = false; // BoxEntity::hit (box_entity.rs:51-70)
+  double closest = t_max;
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i) {
+    int axis;
+    double a0, a1, b0, b1, k, ti;
+    box_side(p, i, axis, a0, a1, b0, b1, k);
+    if (rect_t(axis, a0, a1, b0, b1, k, ro, rd, t_min, closest, ti)) {
+      closest = ti;
+      t = ti;
+      side = (uint32_t)i;
+      any = true;
+    }
+  }
+  return any;
+}
+// Triangle::hit (triangle.rs:48-79)
+YART_DEV bool triangle_t(const double* p, D3 ro, D3 rd, double t_min, double t_max, double& t, double& bu, double& bv) {
+  D3 v0 = d3(p[0], p[1], p[2]), v1 = d3(p[3], p[4], p[5]), v2 = d3(p[6], p[7], p[8]);
+  D3 e1 = v1 - v0, e2 = v2 - v0;
+  D3 h = cross(rd, e2);
+  double a = dot(e1, h);
+  if (a > -kF64Eps && a < kF64Eps) return false;
+  double f = 1.0 / a;
+  D3 s = ro - v0;
+  double u = f * dot(s, h);
+  if (u < 0.0 || u > 1.0) return false;
+  D3 q = cross(s, e1);
+  double v = f * dot(rd, q);
+  if (v < 0.0 || u + v > 1.0) return false;
+  t = f * dot(e2, q);
+  if (t < t_min || t > t_max) return false;
+  bu = u;
+  bv = v;
+  return true;
+}
+
+// ray into the space of Translate(RotateY(.)) (hittable.rs:137-143, 218-227)
+YART_DEV void to_object_space(const yart_object& o, D3& ro, D3& rd) {
+  if (o.wrap & YART_WRAP_TRANSLATE) ro = ro - d3(o.offset[0], o.offset[1], o.offset[2]);
+  if (o.wrap & YART_WRAP_ROTATE_Y) {
+    const double ct = o.cos_theta, st = o.sin_theta;
+    D3 org = ro, dir = rd;
+    org.x = ct * ro.x - st * ro.z;
+    org.z = st * ro.x + ct * ro.z;
+    dir.x = ct * rd.x - st * rd.z;
+    dir.z = st * rd.x + ct * rd.z;
+    ro = org;
+    rd = dir;
+  }
+}
+
+// one primitive record without wrappers; `prim` encodes what the shade stage needs
+YART_DEV bool prim_hit_t(const yart_object& o, D3 ro, D3 rd, double time, double t_min, double t_max, double& t,
+                         uint32_t& prim, double& bu, double& bv) {
+  prim = 0;
+  bu = bv = 0.0;
+  switch (o.kind) {
+    case YART_OBJ_SPHERE: return sphere_t(d3(o.p[0], o.p[1], o.p[2]), o.p[3], ro, rd, t_min, t_max, t);
+    case YART_OBJ_MOVING_SPHERE: return sphere_t(moving_center(o, time), o.p[8], ro, rd, t_min, t_max, t);
+    case YART_OBJ_XY_RECT:
+    case YART_OBJ_XZ_RECT:
+    case YART_OBJ_YZ_RECT: return rect_t(rect_axis(o.kind), o.p[0], o.p[1], o.p[2], o.p[3], o.p[4], ro, rd, t_min, t_max, t);
+    case YART_OBJ_BOX: return box_t(o.p, ro, rd, t_min, t_max, t, prim);
+    case YART_OBJ_TRIANGLE: return triangle_t(o.p, ro, rd, t_min, t_max, t, bu, bv);
+    default: return false;
+  }
+}
+
+// BVHNode group (bvh.rs:151-215): the closest member; prim = member*8 + box side
+YART_DEV bool group_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd, double time, double t_min,
+                          double t_max, double& t, uint32_t& prim) {
+  const DevGroup g = S.groups[o.index];
+  bool any = false;
+  double closest = t_max;
+  if (g.root == 0xFFFFFFFFu) {
+    for (uint32_t i = 0; i < g.n_members; ++i) {
+      double ti, bu, bv;
+      uint32_t pr;
+      if (prim_hit_t(g.members[i], ro, rd, time, t_min, closest, ti, pr, bu, bv)) {
+        closest = ti; t = ti; prim = i * 8 + pr; any = true;
+      }
+    }
+    return any;
+  }
+  // flat 4-wide tree over member boxes; visiting order does not change the closest member
+  uint32_t stack[24];
+  int sp = 0;
+  stack[sp++] = g.root;
+  const double ix = 1.0 / rd.x, iy = 1.0 / rd.y, iz = 1.0 / rd.z;
+  while (sp > 0) {
+    const uint32_t id = stack[--sp];
+    if (id >> 31) {
+      const uint32_t count = (id >> 27) & 0xF, first = id & 0x7FFFFFFu;
+      for (uint32_t i = first; i < first + count; ++i) {
+        double ti, bu, bv;
+        uint32_t pr;
+        if (prim_hit_t(g.members[i], ro, rd, time, t_min, closest, ti, pr, bu, bv)) {
+          closest = ti; t = ti; prim = i * 8 + pr; any = true;
+        }
+      }
+    } else {
+      const float4* nd = g.nodes + (size_t)id * 8;
+      const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 1), mnz = __ldg(nd + 2);
+      const float4 mxx = __ldg(nd + 3), mxy = __ldg(nd + 4), mxz = __ldg(nd + 5);
+      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(nd + 6));
+      const float lo[4][3] = {{mnx.x, mny.x, mnz.x}, {mnx.y, mny.y, mnz.y}, {mnx.z, mny.z, mnz.z}, {mnx.w, mny.w, mnz.w}};
+      const float hi[4][3] = {{mxx.x, mxy.x, mxz.x}, {mxx.y, mxy.y, mxz.y}, {mxx.z, mxy.z, mxz.z}, {mxx.w, mxy.w, mxz.w}};
+      const uint32_t cid[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (cid[k] == 0xFFFFFFFFu) continue;
+        // group boxes are padded outward by the builder, so a conservative >= test is safe
+        double t0 = ((double)lo[k][0] - ro.x) * ix, t1 = ((double)hi[k][0] - ro.x) * ix;
+        double tn = fmax(t_min, fmin(t0, t1)), tf = fmin(closest, fmax(t0, t1));
+        t0 = ((double)lo[k][1] - ro.y) * iy; t1 = ((double)hi[k][1] - ro.y) * iy;
+        tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
+        t0 = ((double)lo[k][2] - ro.z) * iz; t1 = ((double)hi[k][2] - ro.z) * iz;
+        tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
+        if (tf >= tn && sp < 24) stack[sp++] = cid[k];
+      }
+    }
+  }
+  return any;
+}
+
+// Translate(RotateY(FlipFace(prim))) -- t only
+YART_DEV bool inner_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd, double time, double t_min,
+                          double t_max, double& t, uint32_t& prim, double& bu, double& bv) {
+  to_object_space(o, ro, rd);
+  if (o.kind == YART_OBJ_GROUP) {
+    bu = bv = 0.0;
+    return group_hit_t(S, o, ro, rd, time, t_min, t_max, t, prim);
+  }
+  return prim_hit_t(o, ro, rd, time, t_min, t_max, t, prim, bu, bv);
+}
+
+// one non-mesh world object incl. ConstantMedium::hit (hittable.rs:274-321)
+YART_DEV bool object_hit_t(const DevScene& S, const yart_object& o, uint32_t obj_index, D3 ro, D3 rd, double time,
+                           double t_min, double t_max, const Rng& rng, uint32_t bounce, double& t, uint32_t& prim,
+                           double& bu, double& bv) {
+  if (!(o.wrap & YART_WRAP_MEDIUM)) return inner_hit_t(S, o, ro, rd, time, t_min, t_max, t, prim, bu, bv);
+  double t1, t2, b0, b1;
+  uint32_t pr;
+  if (!inner_hit_t(S, o, ro, rd, time, -d_inf(), d_inf(), t1, pr, b0, b1)) return false;
+  if (!inner_hit_t(S, o, ro, rd, time, t1 + 0.0001, d_inf(), t2, pr, b0, b1)) return false;
+  if (t1 < t_min) t1 = t_min;
+  if (t2 > t_max) t2 = t_max;
+  if (!(t1 < t2)) return false;
+  if (t1 < 0.0) t1 = 0.0;
+  const double ray_length = length(rd);
+  const double distance_inside = (t2 - t1) * ray_length;
+  double u0, u1;
+  rng_draw(rng, bounce, YART_SLOT_MEDIUM + obj_index, u0, u1);
+  const double hit_distance = o.neg_inv_density * log(u0);
+  if (!(hit_distance < distance_inside)) return false;
+  t = t1 + hit_distance / ray_length;
+  prim = 0;
+  bu = bv = 0.0;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the traversal kernel
+// ---------------------------------------------------------------------------------------------
+struct TraceParams {
+  DevScene scene;
+  const yart_object* objects; // the list to walk: the world, or a 1-entry list for a mesh-only query
+  uint32_t n_objects;
+  uint32_t media_mask;        // 1 if any object carries YART_WRAP_MEDIUM (needs the Philox stream)
+  const yart_ray* rays;       // indexed by ray id
+  const double* ray_time;     // indexed by ray id, may be null (time 0)
+  const uint32_t* queue;      // work item -> ray id, null = identity
+  const uint32_t* n_items_dev; // number of work items in device memory, null = use n_items
+  uint64_t n_items;
+  uint32_t* work_counter;     // zero before launch
+  DevHit* hits;               // indexed by ray id          (renderer)
+  yart_hit* hits_export;      // indexed by ray id, or null (yart_closest_hit)
+  unsigned long long* counters; // [0] node visits, [1] triangle tests (COUNT only)
+  double t_min, t_max;
+  uint64_t seed;              // Philox key for media inside world.hit
+  uint32_t bounce;
+  uint32_t spp_batch;         // ray id -> (pixel, sample) = (id / spp_batch, sample_base + id % spp_batch)
+  uint32_t sample_base;
+  uint32_t pixel_base;
+};
+
+// finalise one ray for yart_closest_hit: original triangle id and front_face as the reference's
+// HitRecord would carry them (qbvh.rs:452-489, triangle.rs:80-91 etc.)
+__device__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim, double bu,
+                           double bv);
+
+template <bool NEAR, bool COUNT, int STACK>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceParams P) {
+  __shared__ uint32_t s_stack[STACK][kTraceThreads];
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31;
+  const uint64_t n_items = P.n_items_dev ? (uint64_t)*P.n_items_dev : P.n_items;
+
+  // ---- lane state ----
+  uint32_t ray_id = YART_MISS; // YART_MISS = idle
+  uint32_t next_obj = 0;       // next object of the list to start
+  uint32_t cur = kSentinel;    // current stack top (node or leaf id), kSentinel = not traversing
+  int sp = 0;
+  double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0; // ray in the mesh's space
+  uint32_t sgn = 0;
+  const float4* nodes = nullptr;
+  const float4* tris = nullptr;
+  double t_best = 0, t_entry = 0, best_bu = 0, best_bv = 0;
+  uint32_t best_obj = YART_MISS, best_prim = 0, cur_obj = 0;
+  bool exhausted = false; // the global queue is empty
+  unsigned long long n_nodes = 0, n_tris = 0;
+
+  for (;;) {
+    // =============== phase A: advance through the object list / retire / fetch =================
+    if (cur == kSentinel && !(exhausted && ray_id == YART_MISS)) {
+      for (;;) {
+        if (ray_id == YART_MISS) {
+          if (exhausted) break;
+          const uint32_t mask = __activemask();
+          const int leader = __ffs(mask) - 1;
+          const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+          uint32_t base = 0;
+          if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(mask));
+          base = __shfl_sync(mask, base, leader);
+          const uint64_t item = (uint64_t)base + rank;
+          if (item >= n_items) {
+            exhausted = true;
+            break;
+          }
+          ray_id = P.queue ? P.queue[item] : (uint32_t)item;
+          next_obj = 0;
+          t_best = P.t_max;
+          best_obj = YART_MISS;
+          best_prim = 0;
+          best_bu = best_bv = 0.0;
+        }
+        // walk the list until a mesh needs traversal or the list ends
+        bool started = false;
+        const yart_ray wr = P.rays[ray_id];
+        const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
+        const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+        while (next_obj < P.n_objects) {
+          const yart_object& o = P.objects[next_obj];
+          const uint32_t oi = next_obj++;
+          if (o.kind == YART_OBJ_MESH && !(o.wrap & YART_WRAP_MEDIUM)) {
+            D3 ro = wo, rd = wd;
+            to_object_space(o, ro, rd);
+            const DevMesh m = P.scene.meshes[o.index];
+            nodes = m.nodes;
+            tris = m.tris;
+            ox = ro.x; oy = ro.y; oz = ro.z;
+            dx = rd.x; dy = rd.y; dz = rd.z;
+            ix = 1.0 / dx; iy = 1.0 / dy; iz = 1.0 / dz; // qbvh.rs:403-407
+            sgn = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
+            if (NEAR) sgn ^= 7u;
+            cur = m.root;
+            sp = 0;
+            cur_obj = oi;
+            t_entry = t_best;
+            started = true;
+            break;
+          }
+          double t, bu, bv;
+          uint32_t prim;
+          Rng rng;
+          if (P.media_mask) {
+            const uint32_t pix = P.pixel_base + ray_id / P.spp_batch, smp = P.sample_base + ray_id % P.spp_batch;
+            rng = make_rng(P.seed, pix, smp);
+          } else {
+            rng = make_rng(0, 0, 0);
+          }
+          const double time = P.ray_time ? P.ray_time[ray_id] : 0.0;
+          if (object_hit_t(P.scene, o, oi, wo, wd, time, P.t_min, t_best, rng, P.bounce, t, prim, bu, bv)) {
+            t_best = t; best_obj = oi; best_prim = prim; best_bu = bu; best_bv = bv;
+          }
+        }
+        if (started) break;
+        // list finished: retire this ray
+        if (P.hits_export) {
+          export_hit(P, ray_id, t_best, best_obj, best_prim, best_bu, best_bv);
+        } else {
+          DevHit h;
+          h.t = (best_obj == YART_MISS) ? d_inf() : t_best;
+          h.bu = best_bu; h.bv = best_bv; h.obj = best_obj; h.prim = best_prim;
+          P.hits[ray_id] = h;
+        }
+        ray_id = YART_MISS;
+      }
+    }
+    if (!__any_sync(0xffffffffu, ray_id != YART_MISS)) break;
+
+    // =============== phase B: inner nodes (qbvh.rs:491-534) =====================================
+    while (cur < 0x7FFFFFFFu) { // bit31 clear and not the sentinel
+      const float4* nd = nodes + (size_t)cur * 8;
+      const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 1), mnz = __ldg(nd + 2);
+      const float4 mxx = __ldg(nd + 3), mxy = __ldg(nd + 4), mxz = __ldg(nd + 5);
+      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(nd + 6));
+      const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(nd + 7));
+      if (COUNT) n_nodes++;
+      uint32_t hitmask = 0;
+#define YART_BOX(K, LX, LY, LZ, HX, HY, HZ)                                        \
+  {                                                                                \
+    double t0 = ((double)(LX) - ox) * ix, t1 = ((double)(HX) - ox) * ix;           \
+    double tn = fmax(P.t_min, fmin(t0, t1));                                       \
+    double tf = fmin(NEAR ? d_inf() : t_best, fmax(t0, t1));                       \
+    t0 = ((double)(LY) - oy) * iy; t1 = ((double)(HY) - oy) * iy;                  \
+    tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));                      \
+    t0 = ((double)(LZ) - oz) * iz; t1 = ((double)(HZ) - oz) * iz;                  \
+    tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));                      \
+    const bool h = NEAR ? ((tf > tn) && (t_best >= tn)) : (tf > tn);               \
+    hitmask |= h ? (1u << (K)) : 0u;                                               \
+  }
+      YART_BOX(0, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x)
+      YART_BOX(1, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y)
+      YART_BOX(2, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z)
+      YART_BOX(3, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w)
+#undef YART_BOX
+      // ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]] (qbvh.rs:521-524)
+      const uint32_t idx = (((sgn >> (axes & 3u)) & 1u) << 2) | (((sgn >> ((axes >> 2) & 3u)) & 1u) << 1) |
+                           ((sgn >> ((axes >> 4) & 3u)) & 1u);
+      const uint32_t enc = (uint32_t)(((idx & 4u) ? kOrderHi : kOrderLo) >> (16u * (idx & 3u))) & 0xFFFFu;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { // push_hit_children (qbvh.rs:18-31)
+        const uint32_t i = (enc >> (4 * j)) & 3u;
+        if ((hitmask >> i) & 1u) {
+          const uint32_t c = (i == 0) ? ch.x : ((i == 1) ? ch.y : ((i == 2) ? ch.z : ch.w));
+          s_stack[sp][tid] = c;
+          sp++;
+        }
+      }
+      if (sp == 0) {
+        cur = kSentinel;
+      } else {
+        sp--;
+        cur = s_stack[sp][tid];
+      }
+    }
+
+    // =============== phase C: one leaf (qbvh.rs:413-490) ========================================
+    if (cur != kSentinel) {
+      const uint32_t count = (cur >> 27) & 0xFu;
+      const uint32_t first = cur & 0x7FFFFFFu;
+      if (COUNT) n_tris += count;
+      for (uint32_t j = 0; j < count; ++j) {
+        const uint32_t i = NEAR ? (count - 1u - j) : j;
+        const float4* tp = tris + (size_t)(first + i) * 3;
+        const float4 a0 = __ldg(tp), a1 = __ldg(tp + 1), a2 = __ldg(tp + 2);
+        const double v0x = (double)a0.x, v0y = (double)a0.y, v0z = (double)a0.z;
+        const double e1x = (double)a1.x - v0x, e1y = (double)a1.y - v0y, e1z = (double)a1.z - v0z;
+        const double e2x = (double)a2.x - v0x, e2y = (double)a2.y - v0y, e2z = (double)a2.z - v0z;
+        const double hx = dy * e2z - dz * e2y, hy = dz * e2x - dx * e2z, hz = dx * e2y - dy * e2x;
+        const double a = e1x * hx + e1y * hy + e1z * hz;
+        bool ok = !((a > -kF64Eps) && (a < kF64Eps));
+        const double f = 1.0 / a;
+        const double sx = ox - v0x, sy = oy - v0y, sz = oz - v0z;
+        const double u = f * (sx * hx + sy * hy + sz * hz);
+        ok = ok && (u >= 0.0) && (u <= 1.0);
+        const double qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+        const double v = f * (dx * qx + dy * qy + dz * qz);
+        ok = ok && (v >= 0.0) && ((u + v) <= 1.0);
+        const double t = f * (e2x * qx + e2y * qy + e2z * qz);
+        ok = ok && (t >= P.t_min);
+        // REFERENCE: first found wins (`t_max > t`, qbvh.rs:478).  NEAR: mirrored -- last found wins
+        // among this mesh's equal-t hits, still strictly closer than what earlier objects left.
+        ok = ok && (NEAR ? ((t <= t_best) && (t < t_entry)) : (t_best > t));
+        if (ok) {
+          t_best = t; best_obj = cur_obj; best_prim = first + i; best_bu = u; best_bv = v;
+        }
+      }
+      if (sp == 0) {
+        cur = kSentinel;
+      } else {
+        sp--;
+        cur = s_stack[sp][tid];
+      }
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&P.counters[0], n_nodes);
+    atomicAdd(&P.counters[1], n_tris);
+  }
+}
+
+} // namespace yart

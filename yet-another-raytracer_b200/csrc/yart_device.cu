@@ -1,0 +1,873 @@
+// yart_device.cu -- the device half of the C ABI (include/yart.h): context, scene upload,
+// yart_closest_hit, yart_render, yart_film_finalize, yart_generate_camera_rays.
+//
+// There is no CPU fallback anywhere in this file: every entry point launches the sm_100a
+// kernels of device_trace.cuh / device_shade.cuh or fails with YART_ERR_CUDA.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/yart_spectral_tables.h"
+#include "device_shade.cuh"
+#include "host_common.h"
+
+namespace yart {
+
+// ---------------------------------------------------------------------------------------------
+// export of one finished ray for yart_closest_hit
+// ---------------------------------------------------------------------------------------------
+__device__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim, double bu,
+                           double bv) {
+  yart_hit out;
+  if (obj == YART_MISS) {
+    out.t = d_inf(); out.u = 0.0; out.v = 0.0; out.prim_id = YART_MISS; out.obj_id = YART_MISS; out.front_face = 0;
+    out._pad = 0;
+    P.hits_export[ray_id] = out;
+    return;
+  }
+  const yart_ray wr = P.rays[ray_id];
+  const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
+  const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+  const yart_object& o = P.objects[obj];
+  // rebuild the HitRecord of this object to get front_face exactly as the reference computes it
+  DevScene S = P.scene;
+  S.objects = P.objects;
+  DevHit h;
+  h.t = t; h.bu = bu; h.bv = bv; h.obj = obj; h.prim = prim;
+  HitRec rec;
+  world_record(S, h, wo, wd, P.ray_time ? P.ray_time[ray_id] : 0.0, rec);
+  out.t = t; out.u = bu; out.v = bv; out.obj_id = obj; out.front_face = rec.front_face ? 1u : 0u; out._pad = 0;
+  if (o.wrap & YART_WRAP_MEDIUM) {
+    out.prim_id = 0;
+  } else if (o.kind == YART_OBJ_MESH) {
+    const DevMesh m = P.scene.meshes[o.index];
+    out.prim_id = __float_as_uint(__ldg(m.tris + (size_t)prim * 3).w); // FlatTri.orig
+  } else if (o.kind == YART_OBJ_GROUP) {
+    out.prim_id = P.scene.groups[o.index].member_orig[prim >> 3];
+  } else {
+    out.prim_id = prim;
+  }
+  P.hits_export[ray_id] = out;
+}
+
+namespace {
+
+#define CUDA_TRY(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+      return YART_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// flat 4-wide tree over the members of a BVHNode group (median split on the longest centroid
+// axis; the shape is free -- closest-hit results do not depend on it)
+struct GroupBuilder {
+  std::vector<FlatNode> nodes;
+  std::vector<uint32_t> order;
+  std::vector<float> lo, hi; // [n][3], rounded outward
+  std::vector<double> cen;
+
+  struct Box {
+    float mn[3], mx[3];
+    bool some;
+  };
+  static void member_box(const yart_object& m, double mn[3], double mx[3]) {
+    if (m.kind == YART_OBJ_SPHERE) {
+      const double r = std::fabs(m.p[3]);
+      for (int a = 0; a < 3; ++a) { mn[a] = m.p[a] - r; mx[a] = m.p[a] + r; }
+    } else { // BOX
+      for (int a = 0; a < 3; ++a) { mn[a] = std::fmin(m.p[a], m.p[3 + a]); mx[a] = std::fmax(m.p[a], m.p[3 + a]); }
+    }
+  }
+  void prepare(const yart_object* mem, uint32_t n) {
+    order.resize(n);
+    std::iota(order.begin(), order.end(), 0u);
+    lo.resize((size_t)n * 3);
+    hi.resize((size_t)n * 3);
+    cen.resize((size_t)n * 3);
+    for (uint32_t i = 0; i < n; ++i) {
+      double mn[3], mx[3];
+      member_box(mem[i], mn, mx);
+      for (int a = 0; a < 3; ++a) {
+        float l = (float)mn[a], h = (float)mx[a];
+        // pad outward: the rects of a box have zero thickness and f32 rounding may shrink
+        l = nextafterf(nextafterf(l, -INFINITY), -INFINITY);
+        h = nextafterf(nextafterf(h, INFINITY), INFINITY);
+        lo[(size_t)i * 3 + a] = l;
+        hi[(size_t)i * 3 + a] = h;
+        cen[(size_t)i * 3 + a] = 0.5 * (mn[a] + mx[a]);
+      }
+    }
+  }
+  uint32_t split(size_t a, size_t b) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t i = a; i < b; ++i)
+      for (int k = 0; k < 3; ++k) {
+        mn[k] = std::fmin(mn[k], cen[(size_t)order[i] * 3 + k]);
+        mx[k] = std::fmax(mx[k], cen[(size_t)order[i] * 3 + k]);
+      }
+    uint32_t axis = 0;
+    if (mx[1] - mn[1] > mx[0] - mn[0]) axis = 1;
+    if (mx[2] - mn[2] > std::fmax(mx[1] - mn[1], mx[0] - mn[0])) axis = 2;
+    const double* c = cen.data();
+    std::sort(order.begin() + a, order.begin() + b, [c, axis](uint32_t x, uint32_t y) {
+      const double cx = c[(size_t)x * 3 + axis], cy = c[(size_t)y * 3 + axis];
+      return cx < cy || (cx == cy && x < y);
+    });
+    return axis;
+  }
+  static Box merge(const Box& a, const Box& b) {
+    if (!a.some) return b;
+    if (!b.some) return a;
+    Box r;
+    r.some = true;
+    for (int k = 0; k < 3; ++k) { r.mn[k] = fminf(a.mn[k], b.mn[k]); r.mx[k] = fmaxf(a.mx[k], b.mx[k]); }
+    return r;
+  }
+  Box construct(size_t a, size_t b, uint32_t& id) {
+    const size_t n = b - a;
+    Box none;
+    none.some = false;
+    if (n == 0) { id = 0xFFFFFFFFu; return none; }
+    if (n <= 4) {
+      Box bx;
+      bx.some = true;
+      for (int k = 0; k < 3; ++k) { bx.mn[k] = lo[(size_t)order[a] * 3 + k]; bx.mx[k] = hi[(size_t)order[a] * 3 + k]; }
+      for (size_t i = a + 1; i < b; ++i)
+        for (int k = 0; k < 3; ++k) {
+          bx.mn[k] = fminf(bx.mn[k], lo[(size_t)order[i] * 3 + k]);
+          bx.mx[k] = fmaxf(bx.mx[k], hi[(size_t)order[i] * 3 + k]);
+        }
+      id = (uint32_t)a | (1u << 31) | ((uint32_t)n << 27);
+      return bx;
+    }
+    split(a, b);
+    const size_t mid = a + n / 2;
+    split(a, mid);
+    const size_t lmid = a + (mid - a) / 2;
+    uint32_t ids[4];
+    Box bx[4];
+    bx[0] = construct(a, lmid, ids[0]);
+    bx[1] = construct(lmid, mid, ids[1]);
+    split(mid, b);
+    const size_t rmid = mid + (b - mid) / 2;
+    bx[2] = construct(mid, rmid, ids[2]);
+    bx[3] = construct(rmid, b, ids[3]);
+    FlatNode nd;
+    for (int k = 0; k < 4; ++k) {
+      const bool s = bx[k].some;
+      nd.min_x[k] = s ? bx[k].mn[0] : FLT_MAX; nd.min_y[k] = s ? bx[k].mn[1] : FLT_MAX; nd.min_z[k] = s ? bx[k].mn[2] : FLT_MAX;
+      nd.max_x[k] = s ? bx[k].mx[0] : FLT_MAX; nd.max_y[k] = s ? bx[k].mx[1] : FLT_MAX; nd.max_z[k] = s ? bx[k].mx[2] : FLT_MAX;
+      nd.child[k] = ids[k];
+    }
+    nd.axes = 0;
+    nd.pad[0] = nd.pad[1] = nd.pad[2] = 0;
+    nodes.push_back(nd);
+    id = (uint32_t)nodes.size() - 1;
+    return merge(merge(bx[0], bx[1]), merge(bx[2], bx[3]));
+  }
+};
+
+} // namespace
+} // namespace yart
+
+using namespace yart;
+
+struct yart_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+
+  // scene
+  bool have_scene = false;
+  std::vector<void*> scene_allocs;
+  DevScene scene;
+  yart_object* d_solo = nullptr; // one un-wrapped MESH object per mesh, for mesh-only queries
+  uint32_t n_meshes = 0;
+  uint32_t max_stack = 0;
+  bool has_media = false;
+  double* d_cie = nullptr;
+  double* d_smits = nullptr;
+
+  // work buffers
+  DevBuf rays, hits_export, time, wavelength, throughput, hits, contrib, queue_a, queue_b, counts, work, counters, film,
+      rgba;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+
+  void free_scene() {
+    for (void* p : scene_allocs) cudaFree(p);
+    scene_allocs.clear();
+    have_scene = false;
+    d_solo = nullptr;
+  }
+};
+
+namespace {
+
+template <class T>
+int upload(yart_ctx* ctx, const T* host, size_t n, T** out) {
+  *out = nullptr;
+  if (n == 0) return YART_OK;
+  void* p = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&p, n * sizeof(T)));
+  ctx->scene_allocs.push_back(p);
+  CUDA_TRY(ctx, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = reinterpret_cast<T*>(p);
+  return YART_OK;
+}
+
+DevCamera make_camera(const yart_camera& c) { // Camera::new (camera.rs:41-80), f64 on the host
+  auto sub = [](const double* a, const double* b, double* o) { for (int i = 0; i < 3; ++i) o[i] = a[i] - b[i]; };
+  auto unit = [](double* a) {
+    double l = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    double x = a[0] / l, y = a[1] / l, z = a[2] / l;
+    a[0] = x; a[1] = y; a[2] = z;
+  };
+  auto cross3 = [](const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  DevCamera k;
+  const double theta = c.vfov_degrees * 3.14159265358979323846264338327950288 / 180.0;
+  const double h = std::tan(theta / 2.0);
+  const double vh = 2.0 * h;
+  const double vw = c.aspect_ratio * vh;
+  double w[3], u[3], v[3];
+  sub(c.lookfrom, c.lookat, w);
+  unit(w);
+  cross3(c.vup, w, u);
+  unit(u);
+  cross3(w, u, v);
+  const double fh = c.focus_dist * vw, fv = c.focus_dist * vh;
+  for (int i = 0; i < 3; ++i) {
+    k.origin[i] = c.lookfrom[i];
+    k.u[i] = u[i];
+    k.v[i] = v[i];
+    k.horizontal[i] = fh * u[i];
+    k.vertical[i] = fv * v[i];
+  }
+  for (int i = 0; i < 3; ++i) // origin - horizontal/2 - vertical/2 - focus_dist*w
+    k.llc[i] = k.origin[i] - k.horizontal[i] / 2.0 - k.vertical[i] / 2.0 - c.focus_dist * w[i];
+  k.lens_radius = c.aperture / 2.0;
+  k.time0 = c.time0;
+  k.time1 = c.time1;
+  return k;
+}
+
+int grid_for(yart_ctx* ctx, const void* kernel, int threads, int* grid) {
+  int per_sm = 0;
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  if (per_sm < 1) per_sm = 1;
+  *grid = per_sm * ctx->sm_count; // persistent: exactly one resident wave on the 148 SMs
+  return YART_OK;
+}
+
+typedef void (*TraceKernel)(const TraceParams);
+TraceKernel pick_trace_kernel(bool near, bool count, uint32_t max_stack) {
+  if (max_stack <= 32) {
+    if (near) return count ? k_trace<true, true, 32> : k_trace<true, false, 32>;
+    return count ? k_trace<false, true, 32> : k_trace<false, false, 32>;
+  }
+  if (near) return count ? k_trace<true, true, 64> : k_trace<true, false, 64>;
+  return count ? k_trace<false, true, 64> : k_trace<false, false, 64>;
+}
+
+int launch_trace(yart_ctx* ctx, const TraceParams& P, bool near, bool count) {
+  TraceKernel k = pick_trace_kernel(near, count, ctx->max_stack);
+  int grid = 0;
+  int rc = grid_for(ctx, reinterpret_cast<const void*>(k), kTraceThreads, &grid);
+  if (rc) return rc;
+  k<<<grid, kTraceThreads, 0, ctx->stream>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return YART_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int yart_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int yart_ctx_create(int device, yart_ctx** out) {
+  if (!out) {
+    set_global_error("yart_ctx_create: null argument");
+    return YART_ERR_INVALID;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_global_error(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (this library has no CPU fallback)");
+    return YART_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    set_global_error("yart_ctx_create: device index out of range");
+    return YART_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    set_global_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return YART_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_global_error("this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor));
+    return YART_ERR_CUDA;
+  }
+  yart_ctx* ctx = new yart_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&ctx->d_cie, sizeof(double) * 3 * YART_N_CIE)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&ctx->d_smits, sizeof(double) * 7 * YART_N_BINS)) != cudaSuccess) {
+    set_global_error(std::string("context setup: ") + cudaGetErrorString(e));
+    delete ctx;
+    return YART_ERR_CUDA;
+  }
+  cudaMemcpy(ctx->d_cie, YART_CIE_X, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice);
+  cudaMemcpy(ctx->d_cie + YART_N_CIE, YART_CIE_Y, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice);
+  cudaMemcpy(ctx->d_cie + 2 * YART_N_CIE, YART_CIE_Z, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice);
+  cudaMemcpy(ctx->d_smits, YART_SMITS_BASIS, sizeof(double) * 7 * YART_N_BINS, cudaMemcpyHostToDevice);
+  *out = ctx;
+  return YART_OK;
+}
+
+void yart_ctx_destroy(yart_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->free_scene();
+  DevBuf* bufs[] = {&ctx->rays, &ctx->hits_export, &ctx->time, &ctx->wavelength, &ctx->throughput, &ctx->hits, &ctx->contrib,
+                    &ctx->queue_a, &ctx->queue_b, &ctx->counts, &ctx->work, &ctx->counters, &ctx->film, &ctx->rgba};
+  for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->d_cie) cudaFree(ctx->d_cie);
+  if (ctx->d_smits) cudaFree(ctx->d_smits);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* yart_last_error(const yart_ctx* ctx) { return ctx ? ctx->err.c_str() : yart_last_error_global(); }
+
+int yart_ctx_set_stream(yart_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return YART_OK;
+}
+
+int yart_ctx_synchronize(yart_ctx* ctx) {
+  if (!ctx) return YART_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return YART_OK;
+}
+
+int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
+  if (!ctx || !d) return YART_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->free_scene();
+  // ---- validation (the reference would panic on these) ----
+  ctx->has_media = false;
+  auto check_obj = [&](const yart_object& o, bool member) -> const char* {
+    if (o.kind > YART_OBJ_GROUP) return "unknown object kind";
+    if (member && (o.wrap != 0 || (o.kind != YART_OBJ_SPHERE && o.kind != YART_OBJ_BOX)))
+      return "group members must be plain spheres or boxes";
+    if (!member && o.material >= d->n_materials) return "object refers to a missing material";
+    if (o.kind == YART_OBJ_MESH && o.index >= d->n_meshes) return "object refers to a missing mesh";
+    if (o.kind == YART_OBJ_GROUP && o.index >= d->n_groups) return "object refers to a missing group";
+    if ((o.wrap & YART_WRAP_MEDIUM) && (o.kind == YART_OBJ_MESH || o.kind == YART_OBJ_GROUP))
+      return "ConstantMedium around a mesh or group is not supported";
+    return nullptr;
+  };
+  for (uint32_t i = 0; i < d->n_objects; ++i) {
+    if (const char* m = check_obj(d->objects[i], false)) {
+      ctx->err = std::string("yart_ctx_set_scene: object ") + std::to_string(i) + ": " + m;
+      return YART_ERR_INVALID;
+    }
+    if (d->objects[i].wrap & YART_WRAP_MEDIUM) ctx->has_media = true;
+  }
+  for (uint32_t i = 0; i < d->n_materials; ++i) {
+    const yart_material& m = d->materials[i];
+    const bool textured = m.kind == YART_MAT_LAMBERTIAN || m.kind == YART_MAT_METAL || m.kind == YART_MAT_DIFFUSE_LIGHT ||
+                          m.kind == YART_MAT_ISOTROPIC;
+    if (m.kind > YART_MAT_ISOTROPIC || (textured && m.texture >= d->n_textures)) {
+      ctx->err = "yart_ctx_set_scene: bad material " + std::to_string(i);
+      return YART_ERR_INVALID;
+    }
+  }
+  for (uint32_t i = 0; i < d->n_textures; ++i) {
+    const yart_texture& t = d->textures[i];
+    if (t.kind > YART_TEX_IMAGE || (t.kind == YART_TEX_NOISE && t.perlin >= d->n_perlins) ||
+        (t.kind == YART_TEX_IMAGE && t.image >= d->n_images)) {
+      ctx->err = "yart_ctx_set_scene: bad texture " + std::to_string(i);
+      return YART_ERR_INVALID;
+    }
+  }
+  // ---- meshes: QBVH build on the host, flat upload ----
+  std::vector<DevMesh> meshes(d->n_meshes);
+  std::vector<yart_object> solo(d->n_meshes);
+  ctx->max_stack = 0;
+  for (uint32_t i = 0; i < d->n_meshes; ++i) {
+    FlatQbvh q;
+    std::string err;
+    if (!build_qbvh(d->meshes[i], q, err)) {
+      ctx->err = "yart_ctx_set_scene: mesh " + std::to_string(i) + ": " + err;
+      ctx->free_scene();
+      return YART_ERR_INVALID;
+    }
+    FlatNode* dn;
+    FlatTri* dt;
+    FlatTriShade* ds;
+    int rc;
+    if ((rc = upload(ctx, q.nodes.data(), q.nodes.size(), &dn)) || (rc = upload(ctx, q.tris.data(), q.tris.size(), &dt)) ||
+        (rc = upload(ctx, q.shade.data(), q.shade.size(), &ds))) {
+      ctx->free_scene();
+      return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // q goes out of scope
+    meshes[i].nodes = reinterpret_cast<const float4*>(dn);
+    meshes[i].tris = reinterpret_cast<const float4*>(dt);
+    meshes[i].shade = reinterpret_cast<const double*>(ds);
+    meshes[i].root = q.root;
+    meshes[i].max_stack = q.max_stack;
+    ctx->max_stack = std::max(ctx->max_stack, q.max_stack);
+    memset(&solo[i], 0, sizeof(yart_object));
+    solo[i].kind = YART_OBJ_MESH;
+    solo[i].index = i;
+    solo[i].cos_theta = 1.0;
+  }
+  if (ctx->max_stack > 64) {
+    ctx->err = "yart_ctx_set_scene: QBVH deeper than the 64-entry traversal stack (qbvh.rs:382)";
+    ctx->free_scene();
+    return YART_ERR_UNSUPPORTED;
+  }
+  // ---- groups ----
+  std::vector<DevGroup> groups(d->n_groups);
+  for (uint32_t i = 0; i < d->n_groups; ++i) {
+    const yart_group& g = d->groups[i];
+    for (uint32_t k = 0; k < g.n_members; ++k)
+      if (const char* m = check_obj(g.members[k], true)) {
+        ctx->err = std::string("yart_ctx_set_scene: group member: ") + m;
+        ctx->free_scene();
+        return YART_ERR_INVALID;
+      }
+    std::vector<yart_object> members(g.members, g.members + g.n_members);
+    std::vector<uint32_t> orig(g.n_members);
+    std::iota(orig.begin(), orig.end(), 0u);
+    GroupBuilder gb;
+    uint32_t root = 0xFFFFFFFFu;
+    if (g.n_members > 8) {
+      gb.prepare(g.members, g.n_members);
+      gb.construct(0, g.n_members, root);
+      for (uint32_t k = 0; k < g.n_members; ++k) {
+        members[k] = g.members[gb.order[k]];
+        orig[k] = gb.order[k];
+      }
+    }
+    FlatNode* dn;
+    yart_object* dm;
+    uint32_t* dorig;
+    int rc;
+    if ((rc = upload(ctx, gb.nodes.data(), gb.nodes.size(), &dn)) || (rc = upload(ctx, members.data(), members.size(), &dm)) ||
+        (rc = upload(ctx, orig.data(), orig.size(), &dorig))) {
+      ctx->free_scene();
+      return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    groups[i].nodes = reinterpret_cast<const float4*>(dn);
+    groups[i].members = dm;
+    groups[i].member_orig = dorig;
+    groups[i].root = root;
+    groups[i].n_members = g.n_members;
+  }
+  // ---- images ----
+  std::vector<DevImage> images(d->n_images);
+  for (uint32_t i = 0; i < d->n_images; ++i) {
+    uint8_t* dp;
+    int rc = upload(ctx, d->images[i].rgb8, (size_t)d->images[i].width * d->images[i].height * 3, &dp);
+    if (rc) {
+      ctx->free_scene();
+      return rc;
+    }
+    images[i].rgb8 = dp;
+    images[i].width = d->images[i].width;
+    images[i].height = d->images[i].height;
+  }
+  // ---- tables ----
+  DevScene& S = ctx->scene;
+  memset(&S, 0, sizeof(S));
+  yart_object *dobj, *dlights;
+  DevMesh* dmeshes;
+  DevGroup* dgroups;
+  yart_material* dmat;
+  yart_texture* dtex;
+  yart_perlin* dper;
+  DevImage* dimg;
+  int rc;
+  if ((rc = upload(ctx, d->objects, d->n_objects, &dobj)) || (rc = upload(ctx, d->lights, d->n_lights, &dlights)) ||
+      (rc = upload(ctx, meshes.data(), meshes.size(), &dmeshes)) || (rc = upload(ctx, groups.data(), groups.size(), &dgroups)) ||
+      (rc = upload(ctx, d->materials, d->n_materials, &dmat)) || (rc = upload(ctx, d->textures, d->n_textures, &dtex)) ||
+      (rc = upload(ctx, d->perlins, d->n_perlins, &dper)) || (rc = upload(ctx, images.data(), images.size(), &dimg)) ||
+      (rc = upload(ctx, solo.data(), solo.size(), &ctx->d_solo))) {
+    ctx->free_scene();
+    return rc;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  S.objects = dobj;
+  S.lights = dlights;
+  S.meshes = dmeshes;
+  S.groups = dgroups;
+  S.materials = dmat;
+  S.textures = dtex;
+  S.perlins = dper;
+  S.images = dimg;
+  S.cie = ctx->d_cie;
+  S.smits = ctx->d_smits;
+  S.n_objects = d->n_objects;
+  S.n_lights = d->n_lights;
+  for (int k = 0; k < 3; ++k) S.background[k] = d->background_rgb[k];
+  ctx->n_meshes = d->n_meshes;
+  ctx->have_scene = true;
+  return YART_OK;
+}
+
+int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint64_t n, double t_min, double t_max,
+                     uint32_t order, uint32_t flags, yart_hit* hits, yart_stats* stats) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!ctx->have_scene) {
+    ctx->err = "yart_closest_hit: no scene (call yart_ctx_set_scene first)";
+    return YART_ERR_INVALID;
+  }
+  if ((n && (!rays || !hits)) || n > 0xFFFFFFF0ull || order > YART_ORDER_NEAR) {
+    ctx->err = "yart_closest_hit: bad argument";
+    return YART_ERR_INVALID;
+  }
+  if (target != YART_TARGET_WORLD && target >= ctx->n_meshes) {
+    ctx->err = "yart_closest_hit: target is neither a mesh index nor YART_TARGET_WORLD";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return YART_OK;
+  const bool dev = (flags & YART_FLAG_DEVICE_PTRS) != 0;
+  const bool count = (flags & YART_FLAG_COUNT_VISITS) != 0;
+  const yart_ray* d_rays = rays;
+  yart_hit* d_hits = hits;
+  if (!dev) {
+    CUDA_TRY(ctx, ctx->rays.reserve(n * sizeof(yart_ray)));
+    CUDA_TRY(ctx, ctx->hits_export.reserve(n * sizeof(yart_hit)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rays.p, rays, n * sizeof(yart_ray), cudaMemcpyHostToDevice, ctx->stream));
+    d_rays = ctx->rays.as<yart_ray>();
+    d_hits = ctx->hits_export.as<yart_hit>();
+  }
+  CUDA_TRY(ctx, ctx->work.reserve(256));
+  CUDA_TRY(ctx, ctx->counters.reserve(64));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->work.p, 0, 256, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+
+  TraceParams P;
+  memset(&P, 0, sizeof(P));
+  P.scene = ctx->scene;
+  if (target == YART_TARGET_WORLD) {
+    P.objects = ctx->scene.objects;
+    P.n_objects = ctx->scene.n_objects;
+    P.media_mask = ctx->has_media ? 1u : 0u;
+  } else {
+    P.objects = ctx->d_solo + target;
+    P.n_objects = 1;
+    P.media_mask = 0;
+  }
+  P.rays = d_rays;
+  P.n_items = n;
+  P.work_counter = ctx->work.as<uint32_t>();
+  P.hits_export = d_hits;
+  P.counters = ctx->counters.as<unsigned long long>();
+  P.t_min = t_min;
+  P.t_max = t_max;
+  P.seed = 0;
+  P.bounce = 1;
+  P.spp_batch = 1;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = launch_trace(ctx, P, order == YART_ORDER_NEAR, count);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(yart_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long c[2] = {0, 0};
+  if (count) CUDA_TRY(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    stats->rays = n;
+    stats->node_visits = c[0];
+    stats->tri_tests = c[1];
+    stats->kernel_launches = 1;
+    stats->gpu_ms = ms;
+    stats->trace_ms = ms;
+  }
+  return YART_OK;
+}
+
+static int fill_render_params(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, RenderParams& R) {
+  if (o->width < 2 || o->height < 2 || o->sample_end < o->sample_begin || o->max_depth == 0 || o->order > YART_ORDER_NEAR ||
+      (uint64_t)o->width * o->height > 0x7FFFFFFFull) {
+    ctx->err = "render options: need width,height >= 2, sample_begin <= sample_end, max_depth >= 1";
+    return YART_ERR_INVALID;
+  }
+  memset(&R, 0, sizeof(R));
+  R.scene = ctx->scene;
+  R.cam = make_camera(*cam);
+  R.width = o->width;
+  R.height = o->height;
+  R.max_depth = o->max_depth;
+  R.seed = o->seed;
+  return YART_OK;
+}
+
+int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, double* film_xyz, yart_stats* stats) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!ctx->have_scene || !cam || !o || !film_xyz) {
+    ctx->err = "yart_render: missing scene or null argument";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  RenderParams R;
+  int rc = fill_render_params(ctx, cam, o, R);
+  if (rc) return rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  const uint32_t n_pixels_total = o->width * o->height;
+  const uint32_t n_samples = o->sample_end - o->sample_begin;
+  const bool dev = (o->flags & YART_FLAG_DEVICE_PTRS) != 0;
+  const size_t film_bytes = (size_t)n_pixels_total * 3 * sizeof(double);
+  double* d_film = film_xyz;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (!dev) {
+    CUDA_TRY(ctx, ctx->film.reserve(film_bytes));
+    d_film = ctx->film.as<double>();
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_film, film_xyz, film_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  uint64_t total_rays = 0, total_paths = 0, launches = 0;
+  double trace_ms = 0.0;
+  uint32_t deepest = 0;
+  if (n_samples > 0) {
+    // batch shape: whole frame x spp_batch, or pixel chunks when the frame alone is too large
+    const uint64_t kMaxPaths = 1ull << 24; // 16 Mi paths in flight (~2.3 GB of path state)
+    uint32_t spp_batch = o->batch_spp ? o->batch_spp : (uint32_t)std::max<uint64_t>(1, kMaxPaths / n_pixels_total);
+    spp_batch = std::min(spp_batch, n_samples);
+    uint32_t pix_chunk = n_pixels_total;
+    if ((uint64_t)pix_chunk * spp_batch > 4 * kMaxPaths) pix_chunk = (uint32_t)(4 * kMaxPaths / spp_batch);
+    const uint64_t cap = (uint64_t)pix_chunk * spp_batch;
+    CUDA_TRY(ctx, ctx->rays.reserve(cap * sizeof(yart_ray)));
+    CUDA_TRY(ctx, ctx->time.reserve(cap * sizeof(double)));
+    CUDA_TRY(ctx, ctx->wavelength.reserve(cap * sizeof(double)));
+    CUDA_TRY(ctx, ctx->throughput.reserve(cap * sizeof(double)));
+    CUDA_TRY(ctx, ctx->hits.reserve(cap * sizeof(DevHit)));
+    CUDA_TRY(ctx, ctx->contrib.reserve(cap * 3 * sizeof(double)));
+    CUDA_TRY(ctx, ctx->queue_a.reserve(cap * sizeof(uint32_t)));
+    CUDA_TRY(ctx, ctx->queue_b.reserve(cap * sizeof(uint32_t)));
+    const uint32_t D = o->max_depth;
+    const size_t n_counts = (size_t)D + 2;
+    CUDA_TRY(ctx, ctx->counts.reserve(n_counts * sizeof(uint32_t)));
+    CUDA_TRY(ctx, ctx->work.reserve(n_counts * sizeof(uint32_t)));
+    while (ctx->ev_pool.size() < 2 * (size_t)D) {
+      cudaEvent_t e;
+      CUDA_TRY(ctx, cudaEventCreate(&e));
+      ctx->ev_pool.push_back(e);
+    }
+    R.st.rays = ctx->rays.as<yart_ray>();
+    R.st.time = ctx->time.as<double>();
+    R.st.wavelength = ctx->wavelength.as<double>();
+    R.st.throughput = ctx->throughput.as<double>();
+    R.st.hits = ctx->hits.as<DevHit>();
+    R.st.contrib = ctx->contrib.as<double>();
+    uint32_t* counts = ctx->counts.as<uint32_t>();
+    uint32_t* work = ctx->work.as<uint32_t>();
+    std::vector<uint32_t> h_counts(n_counts);
+    const bool near = o->order == YART_ORDER_NEAR;
+    const int stream_grid = ctx->sm_count * 8;
+
+    for (uint32_t s0 = o->sample_begin; s0 < o->sample_end; s0 += spp_batch) {
+      const uint32_t spp = std::min(spp_batch, o->sample_end - s0);
+      for (uint32_t p0 = 0; p0 < n_pixels_total; p0 += pix_chunk) {
+        R.pixel_base = p0;
+        R.n_pixels = std::min(pix_chunk, n_pixels_total - p0);
+        R.sample_base = s0;
+        R.spp_batch = spp;
+        CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, n_counts * sizeof(uint32_t), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(work, 0, n_counts * sizeof(uint32_t), ctx->stream));
+        uint32_t* qa = ctx->queue_a.as<uint32_t>();
+        uint32_t* qb = ctx->queue_b.as<uint32_t>();
+        k_raygen<<<stream_grid, 256, 0, ctx->stream>>>(R, qa, counts + 1);
+        launches++;
+        uint32_t b_done = 0;
+        for (uint32_t b = 1; b <= D; ++b) {
+          TraceParams P;
+          memset(&P, 0, sizeof(P));
+          P.scene = ctx->scene;
+          P.objects = ctx->scene.objects;
+          P.n_objects = ctx->scene.n_objects;
+          P.media_mask = ctx->has_media ? 1u : 0u;
+          P.rays = R.st.rays;
+          P.ray_time = R.st.time;
+          P.queue = qa;
+          P.n_items_dev = counts + b;
+          P.work_counter = work + b;
+          P.hits = R.st.hits;
+          P.t_min = 0.001; // world.hit(ray_in, 0.001, f64::INFINITY) (main.rs:548)
+          P.t_max = INFINITY;
+          P.seed = o->seed;
+          P.bounce = b;
+          P.spp_batch = spp;
+          P.sample_base = s0;
+          P.pixel_base = p0;
+          CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1)], ctx->stream));
+          rc = launch_trace(ctx, P, near, false);
+          if (rc) return rc;
+          CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1) + 1], ctx->stream));
+          k_shade<<<stream_grid, 256, 0, ctx->stream>>>(R, qa, counts + b, qb, counts + b + 1, b);
+          launches += 2;
+          std::swap(qa, qb);
+          b_done = b;
+          // the tail of the bounce loop is nearly empty: look at the live count now and then
+          if (b >= 4 && (b % 4) == 0 && b < D) {
+            uint32_t live = 0;
+            CUDA_TRY(ctx, cudaMemcpyAsync(&live, counts + b + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (live == 0) break;
+          }
+        }
+        k_film_accumulate<<<stream_grid, 256, 0, ctx->stream>>>(R, d_film);
+        launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), counts, n_counts * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        total_paths += h_counts[1];
+        for (uint32_t b = 1; b <= b_done; ++b) {
+          total_rays += h_counts[b];
+          if (h_counts[b]) deepest = std::max(deepest, b);
+          float ms = 0.f;
+          CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_pool[2 * (b - 1)], ctx->ev_pool[2 * (b - 1) + 1]));
+          trace_ms += ms;
+        }
+      }
+    }
+  }
+  if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(film_xyz, d_film, film_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    stats->rays = total_rays;
+    stats->paths = total_paths;
+    stats->kernel_launches = launches;
+    stats->gpu_ms = ms;
+    stats->trace_ms = trace_ms;
+    stats->max_bounce = deepest;
+  }
+  return YART_OK;
+}
+
+int yart_film_finalize(yart_ctx* ctx, const double* film_xyz, uint32_t width, uint32_t height, uint32_t spp, uint32_t flags,
+                       uint8_t* rgba8) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!film_xyz || !rgba8 || !width || !height || !spp) {
+    ctx->err = "yart_film_finalize: bad argument";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)width * height;
+  const bool dev = (flags & YART_FLAG_DEVICE_PTRS) != 0;
+  const double* d_film = film_xyz;
+  uint8_t* d_rgba = rgba8;
+  if (!dev) {
+    CUDA_TRY(ctx, ctx->film.reserve(n * 3 * sizeof(double)));
+    CUDA_TRY(ctx, ctx->rgba.reserve(n * 4));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->film.p, film_xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    d_film = ctx->film.as<double>();
+    d_rgba = ctx->rgba.as<uint8_t>();
+  }
+  k_film_finalize<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_film, width, height, spp, d_rgba);
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(rgba8, d_rgba, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return YART_OK;
+}
+
+int yart_generate_camera_rays(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, yart_ray* rays_host,
+                              double* wavelength_host, double* time_host) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!cam || !o || !rays_host) {
+    ctx->err = "yart_generate_camera_rays: null argument";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  RenderParams R;
+  int rc = fill_render_params(ctx, cam, o, R);
+  if (rc) return rc;
+  const uint32_t ns = o->sample_end - o->sample_begin;
+  const uint64_t n = (uint64_t)o->width * o->height * ns;
+  if (n == 0) return YART_OK;
+  CUDA_TRY(ctx, ctx->rays.reserve(n * sizeof(yart_ray)));
+  CUDA_TRY(ctx, ctx->wavelength.reserve(n * sizeof(double)));
+  CUDA_TRY(ctx, ctx->time.reserve(n * sizeof(double)));
+  R.pixel_base = 0;
+  R.n_pixels = o->width * o->height;
+  R.sample_base = o->sample_begin;
+  R.spp_batch = ns;
+  k_camera_rays<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(R, ctx->rays.as<yart_ray>(), ctx->wavelength.as<double>(),
+                                                            ctx->time.as<double>());
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(rays_host, ctx->rays.p, n * sizeof(yart_ray), cudaMemcpyDeviceToHost, ctx->stream));
+  if (wavelength_host)
+    CUDA_TRY(ctx, cudaMemcpyAsync(wavelength_host, ctx->wavelength.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (time_host) CUDA_TRY(ctx, cudaMemcpyAsync(time_host, ctx->time.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return YART_OK;
+}
+
+} // extern "C"
