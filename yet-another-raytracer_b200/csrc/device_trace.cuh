@@ -161,6 +161,9 @@ YART_DEV bool group_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
         double ti, bu, bv;
         uint32_t pr;
         if (prim_hit_t(g.members[i], ro, rd, time, t_min, closest, ti, pr, bu, bv)) {
+          // spheres and rects accept t == t_max, so in list order the LAST of several equal-t
+          // members wins (adjacent boxes share faces); the tree visits members in another order
+          if (any && ti == closest && g.member_orig[i] < g.member_orig[prim >> 3]) continue;
           closest = ti; t = ti; prim = i * 8 + pr; any = true;
         }
       }
