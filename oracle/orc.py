@@ -64,6 +64,7 @@ def lib():
         "orc_brute_force_hit": (i32, [vp, u32, vp, u64, f64, f64, vp, vp]),
         "orc_tie_set": (i32, [vp, u32, vp, f64, f64, vp, u32, P(u32)]),
         "orc_render": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, P(abi.Stats), i32]),
+        "orc_render_tiles": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, P(abi.Stats), i32, u32, u32]),
         "orc_film_finalize": (i32, [vp, u32, u32, u32, vp]),
         "orc_camera_rays": (i32, [P(abi.Camera), P(abi.RenderOpts), vp, vp, vp]),
         "orc_dump_path_rays": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, u64, P(u64)]),
@@ -152,12 +153,13 @@ class Scene:
         return ids[:min(n.value, 64)].copy()
 
     def render(self, camera, width, height, sample_begin, sample_end, max_depth=50, seed=1, order=abi.ORDER_REFERENCE,
-               n_threads=1, film=None):
+               n_threads=1, film=None, tiles=(0, 64)):
         if film is None:
             film = np.zeros((height, width, 3), dtype=np.float64)
         st = abi.Stats()
         o = _opts(width, height, sample_begin, sample_end, max_depth, seed, order)
-        _check(lib().orc_render(self._h, C.byref(camera), C.byref(o), film.ctypes.data, C.byref(st), n_threads))
+        _check(lib().orc_render_tiles(self._h, C.byref(camera), C.byref(o), film.ctypes.data, C.byref(st), n_threads,
+                                      tiles[0], tiles[1]))
         return film, st
 
     def dump_path_rays(self, camera, width, height, sample_begin, sample_end, cap, max_depth=50, seed=1):

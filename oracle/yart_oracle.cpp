@@ -1381,26 +1381,41 @@ int orc_tie_set(const orc_scene* s, uint32_t mesh, const yart_ray* ray, double t
   return YART_OK;
 }
 
+int orc_render_tiles(const orc_scene* s, const yart_camera* cam, const yart_render_opts* o, double* film,
+                     yart_stats* stats, int n_threads, uint32_t tile_begin, uint32_t tile_end);
+
 int orc_render(const orc_scene* s, const yart_camera* cam, const yart_render_opts* o, double* film,
                yart_stats* stats, int n_threads) {
+  return orc_render_tiles(s, cam, o, film, stats, n_threads, 0, 64);
+}
+
+// the same loop restricted to jobs [tile_begin, tile_end) of the 64 tile jobs (main.rs:636-646),
+// so a bounded SAMPLE of a big frame can be timed as the CPU baseline
+int orc_render_tiles(const orc_scene* s, const yart_camera* cam, const yart_render_opts* o, double* film,
+                     yart_stats* stats, int n_threads, uint32_t tile_begin, uint32_t tile_end) {
   if (!s || !cam || !o || !film) { g_err = "null argument"; return YART_ERR_INVALID; }
   if (o->width < 2 || o->height < 2) { g_err = "width/height must be >= 2"; return YART_ERR_INVALID; }
   if (n_threads < 1) n_threads = 1;
   const Camera k = make_camera(*cam);
   const uint32_t W = o->width, H = o->height;
+  if (tile_end > 64) tile_end = 64;
+  // jobs are handed out in row-bands of each tile so a small tile range still feeds all workers
   std::atomic<uint32_t> next_job(0);
   std::atomic<uint64_t> total_rays(0), total_paths(0);
+  const uint32_t bands = 8;
+  const uint32_t n_jobs = (tile_end > tile_begin ? tile_end - tile_begin : 0) * bands;
   auto worker = [&]() {
     std::vector<Factor> scratch;
     HitCtx c{&s->s, o->order, nullptr};
     uint64_t rays = 0, paths = 0;
     for (;;) {
-      uint32_t job = next_job.fetch_add(1);
-      if (job >= 64) break;
+      uint32_t jb = next_job.fetch_add(1);
+      if (jb >= n_jobs) break;
+      uint32_t job = tile_begin + jb / bands, band = jb % bands;
       uint32_t col = job / 8, row = job % 8; // main.rs:636-646
       uint32_t crop_x = (uint32_t)((uint64_t)W * col / 8), crop_y = (uint32_t)((uint64_t)H * row / 8);
       uint32_t cw = W / 8, ch = H / 8;
-      for (uint32_t y = 0; y < ch; ++y)
+      for (uint32_t y = ch * band / bands; y < ch * (band + 1) / bands; ++y)
         for (uint32_t x = 0; x < cw; ++x) {
           uint32_t px = x + crop_x, py = y + crop_y;
           double* pix = film + ((size_t)py * W + px) * 3;

@@ -65,6 +65,10 @@ int orc_tie_set(const orc_scene* s, uint32_t mesh, const yart_ray* ray, double t
 /* render() sample loop (main.rs:590-718), 8x8 tiles on n_threads workers */
 int orc_render(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
                double* film_xyz, yart_stats* stats, int n_threads);
+/* jobs [tile_begin, tile_end) of the 64 tile jobs only: a bounded sample of a big frame */
+int orc_render_tiles(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
+                     double* film_xyz, yart_stats* stats, int n_threads, uint32_t tile_begin,
+                     uint32_t tile_end);
 int orc_film_finalize(const double* film_xyz, uint32_t width, uint32_t height, uint32_t spp,
                       uint8_t* rgba8);
 int orc_camera_rays(const yart_camera* cam, const yart_render_opts* opts, yart_ray* rays,

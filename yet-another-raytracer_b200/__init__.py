@@ -288,21 +288,24 @@ class Context:
         return o
 
     def render(self, camera, width, height, sample_begin, sample_end, max_depth=50, seed=1, order=ORDER_NEAR,
-               batch_spp=0, film=None):
+               batch_spp=0, film=None, count_visits=False):
         """Batched sample loop of `render` (reference main.rs:650-708).  Returns (film, stats);
-        film is the (H, W, 3) f64 sum of sanitised XYZ samples (continued if `film` is given)."""
+        film is the (H, W, 3) f64 sum of sanitised XYZ samples (continued if `film` is given;
+        pass a pinned buffer for fast host<->device copies)."""
         if film is None:
             film = np.zeros((height, width, 3), dtype=np.float64)
         assert film.dtype == np.float64 and film.shape == (height, width, 3) and film.flags.c_contiguous
         st = abi.Stats()
-        o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp, 0)
+        o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp,
+                       FLAG_COUNT_VISITS if count_visits else 0)
         self._check(_lib.yart_render(self._h, C.byref(camera), C.byref(o), film.ctypes.data, C.byref(st)))
         return film, st
 
     def render_device(self, camera, width, height, sample_begin, sample_end, film_ptr, max_depth=50, seed=1,
-                      order=ORDER_NEAR, batch_spp=0):
+                      order=ORDER_NEAR, batch_spp=0, count_visits=False):
         st = abi.Stats()
-        o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp, FLAG_DEVICE_PTRS)
+        o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp,
+                       FLAG_DEVICE_PTRS | (FLAG_COUNT_VISITS if count_visits else 0))
         self._check(_lib.yart_render(self._h, C.byref(camera), C.byref(o), C.c_void_p(film_ptr), C.byref(st)))
         return st
 

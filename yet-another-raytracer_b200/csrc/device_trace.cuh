@@ -251,19 +251,72 @@ struct TraceParams {
   uint32_t spp_batch;         // ray id -> (pixel, sample) = (id / spp_batch, sample_base + id % spp_batch)
   uint32_t sample_base;
   uint32_t pixel_base;
+  uint32_t refill_threshold;  // run the fetch/advance phase once this many lanes wait for it
+  uint32_t node_threshold;    // leave the inner-node loop once fewer lanes than this are in it
 };
 
 // finalise one ray for yart_closest_hit: original triangle id and front_face as the reference's
 // HitRecord would carry them (qbvh.rs:452-489, triangle.rs:80-91 etc.)
-__device__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim, double bu,
-                           double bv);
+__device__ __noinline__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim,
+                                        double bu, double bv);
+
+// every non-mesh object of the list, out of line: keeps spheres / boxes / media / groups and their
+// registers out of the traversal loop
+__device__ __noinline__ bool object_hit_outlined(const TraceParams& P, const yart_object& o, uint32_t oi, uint32_t ray_id,
+                                                 D3 wo, D3 wd, double t_best, double& t, uint32_t& prim, double& bu,
+                                                 double& bv) {
+  Rng rng;
+  if (P.media_mask) {
+    const uint32_t pix = P.pixel_base + ray_id / P.spp_batch, smp = P.sample_base + ray_id % P.spp_batch;
+    rng = make_rng(P.seed, pix, smp);
+  } else {
+    rng = make_rng(0, 0, 0);
+  }
+  const double time = P.ray_time ? P.ray_time[ray_id] : 0.0;
+  return object_hit_t(P.scene, o, oi, wo, wd, time, P.t_min, t_best, rng, P.bounce, t, prim, bu, bv);
+}
+
+// min / max for values that cannot be NaN: one DSETP + selects instead of the IEEE minNum/maxNum
+// sequence (DSETP.MIN + SEL + FSEL + NaN quieting) the compiler emits for fmin/fmax on doubles
+YART_DEV double min_nn(double a, double b) { return a < b ? a : b; }
+YART_DEV double max_nn(double a, double b) { return a > b ? a : b; }
+
+// The four slab tests of one node exactly as qbvh.rs:495-519 with IEEE minNum/maxNum folds -- the
+// path for rays with a zero or non-finite component, whose slabs can be NaN (0 * inf).  Out of line:
+// it is rare and its temporaries must not cost the common path registers.
+template <bool NEAR>
+__device__ __noinline__ uint32_t box4_ieee(const float4* nd, double ox, double oy, double oz, double ix, double iy,
+                                           double iz, double t_min, double t_best) {
+  const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 1), mnz = __ldg(nd + 2);
+  const float4 mxx = __ldg(nd + 3), mxy = __ldg(nd + 4), mxz = __ldg(nd + 5);
+  uint32_t hitmask = 0;
+#define YART_BOX(K, LX, LY, LZ, HX, HY, HZ)                                        \
+  {                                                                                \
+    double t0 = ((double)(LX) - ox) * ix, t1 = ((double)(HX) - ox) * ix;           \
+    double tn = fmax(t_min, fmin(t0, t1));                                         \
+    double tf = fmin(NEAR ? d_inf() : t_best, fmax(t0, t1));                       \
+    t0 = ((double)(LY) - oy) * iy; t1 = ((double)(HY) - oy) * iy;                  \
+    tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));                      \
+    t0 = ((double)(LZ) - oz) * iz; t1 = ((double)(HZ) - oz) * iz;                  \
+    tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));                      \
+    const bool h = NEAR ? ((tf > tn) && (t_best >= tn)) : (tf > tn);               \
+    hitmask |= h ? (1u << (K)) : 0u;                                               \
+  }
+  YART_BOX(0, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x)
+  YART_BOX(1, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y)
+  YART_BOX(2, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z)
+  YART_BOX(3, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w)
+#undef YART_BOX
+  return hitmask;
+}
 
 template <bool NEAR, bool COUNT, int STACK>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceParams P) {
-  __shared__ uint32_t s_stack[STACK][kTraceThreads];
+__global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P) {
+  __shared__ uint32_t s_stack[STACK + 1][kTraceThreads];
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31;
   const uint64_t n_items = P.n_items_dev ? (uint64_t)*P.n_items_dev : P.n_items;
+  const uint32_t RT = P.refill_threshold, NT = P.node_threshold;
 
   // ---- lane state ----
   uint32_t ray_id = YART_MISS; // YART_MISS = idle
@@ -271,7 +324,9 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceParams P) {
   uint32_t cur = kSentinel;    // current stack top (node or leaf id), kSentinel = not traversing
   int sp = 0;
   double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0; // ray in the mesh's space
-  uint32_t sgn = 0;
+  uint32_t sgn = 0;            // ORDER_TABLE sign bits (mirrored when NEAR)
+  uint32_t near_x = 0, near_y = 1, near_z = 2; // float4 index of the plane the ray enters first, per axis
+  bool weird = false;          // a zero / non-finite component: slabs can be NaN, take the IEEE path
   const float4* nodes = nullptr;
   const float4* tris = nullptr;
   double t_best = 0, t_entry = 0, best_bu = 0, best_bv = 0;
@@ -281,7 +336,12 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceParams P) {
 
   for (;;) {
     // =============== phase A: advance through the object list / retire / fetch =================
-    if (cur == kSentinel && !(exhausted && ray_id == YART_MISS)) {
+    // Batched: lanes that finished a traversal wait until RT of them can run this (long, divergent)
+    // code together, unless nobody else has work.
+    const bool want_a = (cur == kSentinel) && !(exhausted && ray_id == YART_MISS);
+    const uint32_t a_mask = __ballot_sync(0xffffffffu, want_a);
+    const uint32_t busy_mask = __ballot_sync(0xffffffffu, cur != kSentinel);
+    if (want_a && ((uint32_t)__popc(a_mask) >= RT || busy_mask == 0)) {
       for (;;) {
         if (ray_id == YART_MISS) {
           if (exhausted) break;
@@ -320,8 +380,13 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceParams P) {
             ox = ro.x; oy = ro.y; oz = ro.z;
             dx = rd.x; dy = rd.y; dz = rd.z;
             ix = 1.0 / dx; iy = 1.0 / dy; iz = 1.0 / dz; // qbvh.rs:403-407
-            sgn = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
-            if (NEAR) sgn ^= 7u;
+            const uint32_t pos = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
+            sgn = NEAR ? (pos ^ 7u) : pos;
+            near_x = (pos & 1u) ? 0u : 3u;
+            near_y = (pos & 2u) ? 1u : 4u;
+            near_z = (pos & 4u) ? 2u : 5u;
+            // (b - o) * (1/d) can only be NaN when 1/d is infinite or the ray itself is not finite
+            weird = !(isfinite(ix) && isfinite(iy) && isfinite(iz) && isfinite(ox) && isfinite(oy) && isfinite(oz));
             cur = m.root;
             sp = 0;
             cur_obj = oi;
@@ -331,15 +396,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceParams P) {
           }
           double t, bu, bv;
           uint32_t prim;
-          Rng rng;
-          if (P.media_mask) {
-            const uint32_t pix = P.pixel_base + ray_id / P.spp_batch, smp = P.sample_base + ray_id % P.spp_batch;
-            rng = make_rng(P.seed, pix, smp);
-          } else {
-            rng = make_rng(0, 0, 0);
-          }
-          const double time = P.ray_time ? P.ray_time[ray_id] : 0.0;
-          if (object_hit_t(P.scene, o, oi, wo, wd, time, P.t_min, t_best, rng, P.bounce, t, prim, bu, bv)) {
+          if (object_hit_outlined(P, o, oi, ray_id, wo, wd, t_best, t, prim, bu, bv)) {
             t_best = t; best_obj = oi; best_prim = prim; best_bu = bu; best_bv = bv;
           }
         }
@@ -359,54 +416,72 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceParams P) {
     if (!__any_sync(0xffffffffu, ray_id != YART_MISS)) break;
 
     // =============== phase B: inner nodes (qbvh.rs:491-534) =====================================
-    while (cur < 0x7FFFFFFFu) { // bit31 clear and not the sentinel
-      const float4* nd = nodes + (size_t)cur * 8;
-      const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 1), mnz = __ldg(nd + 2);
-      const float4 mxx = __ldg(nd + 3), mxy = __ldg(nd + 4), mxz = __ldg(nd + 5);
-      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(nd + 6));
-      const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(nd + 7));
-      if (COUNT) n_nodes++;
-      uint32_t hitmask = 0;
-#define YART_BOX(K, LX, LY, LZ, HX, HY, HZ)                                        \
-  {                                                                                \
-    double t0 = ((double)(LX) - ox) * ix, t1 = ((double)(HX) - ox) * ix;           \
-    double tn = fmax(P.t_min, fmin(t0, t1));                                       \
-    double tf = fmin(NEAR ? d_inf() : t_best, fmax(t0, t1));                       \
-    t0 = ((double)(LY) - oy) * iy; t1 = ((double)(HY) - oy) * iy;                  \
-    tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));                      \
-    t0 = ((double)(LZ) - oz) * iz; t1 = ((double)(HZ) - oz) * iz;                  \
-    tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));                      \
-    const bool h = NEAR ? ((tf > tn) && (t_best >= tn)) : (tf > tn);               \
-    hitmask |= h ? (1u << (K)) : 0u;                                               \
+    // Warp-uniform loop: keep stepping while at least NT lanes are on inner nodes; with fewer, yield to
+    // the leaf / refill phases if they have something to do.
+    for (;;) {
+      const bool has_node = cur < 0x7FFFFFFFu; // bit31 clear and not the sentinel
+      const uint32_t nm = __ballot_sync(0xffffffffu, has_node);
+      if (nm == 0) break;
+      if ((uint32_t)__popc(nm) < NT) {
+        const uint32_t lm = __ballot_sync(0xffffffffu, cur >= 0x80000000u);
+        const uint32_t wm = __ballot_sync(0xffffffffu, (cur == kSentinel) && !(exhausted && ray_id == YART_MISS));
+        if (lm != 0 || (uint32_t)__popc(wm) >= RT) break;
+      }
+      if (has_node) {
+        const float4* nd = nodes + (size_t)cur * 8;
+        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(nd + 6));
+        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(nd + 7));
+        if (COUNT) n_nodes++;
+        uint32_t hitmask = 0;
+        if (!weird) {
+          // Fast path.  All slab values are finite or +-inf, never NaN, and b_min <= b_max, so
+          // min(t0,t1) is the plane on the side the ray comes from and max(t0,t1) the other one:
+          // identical values to qbvh.rs:495-519 with half the min/max work and no NaN handling.
+          const float4 nx = __ldg(nd + near_x), ny = __ldg(nd + near_y), nz = __ldg(nd + near_z);
+          const float4 fx = __ldg(nd + (3u - near_x)), fy = __ldg(nd + (5u - near_y)), fz = __ldg(nd + (7u - near_z));
+#define YART_BOX_FAST(K, C)                                                                              \
+  {                                                                                                      \
+    double tn = max_nn(P.t_min, ((double)nx.C - ox) * ix);                                               \
+    tn = max_nn(tn, ((double)ny.C - oy) * iy);                                                           \
+    tn = max_nn(tn, ((double)nz.C - oz) * iz);                                                           \
+    double tf = NEAR ? ((double)fx.C - ox) * ix : min_nn(t_best, ((double)fx.C - ox) * ix);             \
+    tf = min_nn(tf, ((double)fy.C - oy) * iy);                                                           \
+    tf = min_nn(tf, ((double)fz.C - oz) * iz);                                                           \
+    const bool h = NEAR ? ((tf > tn) && (t_best >= tn)) : (tf > tn);                                     \
+    hitmask |= h ? (1u << (K)) : 0u;                                                                     \
   }
-      YART_BOX(0, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x)
-      YART_BOX(1, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y)
-      YART_BOX(2, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z)
-      YART_BOX(3, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w)
-#undef YART_BOX
-      // ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]] (qbvh.rs:521-524)
-      const uint32_t idx = (((sgn >> (axes & 3u)) & 1u) << 2) | (((sgn >> ((axes >> 2) & 3u)) & 1u) << 1) |
-                           ((sgn >> ((axes >> 4) & 3u)) & 1u);
-      const uint32_t enc = (uint32_t)(((idx & 4u) ? kOrderHi : kOrderLo) >> (16u * (idx & 3u))) & 0xFFFFu;
+          YART_BOX_FAST(0, x)
+          YART_BOX_FAST(1, y)
+          YART_BOX_FAST(2, z)
+          YART_BOX_FAST(3, w)
+#undef YART_BOX_FAST
+        } else {
+          hitmask = box4_ieee<NEAR>(nd, ox, oy, oz, ix, iy, iz, P.t_min, t_best);
+        }
+        // ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]] (qbvh.rs:521-524)
+        const uint32_t idx = (((sgn >> (axes & 3u)) & 1u) << 2) | (((sgn >> ((axes >> 2) & 3u)) & 1u) << 1) |
+                             ((sgn >> ((axes >> 4) & 3u)) & 1u);
+        const uint32_t enc = (uint32_t)(((idx & 4u) ? kOrderHi : kOrderLo) >> (16u * (idx & 3u))) & 0xFFFFu;
+        // push_hit_children (qbvh.rs:18-31), branch-free: always store to the next free slot, advance
+        // the cursor only for hit lanes
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { // push_hit_children (qbvh.rs:18-31)
-        const uint32_t i = (enc >> (4 * j)) & 3u;
-        if ((hitmask >> i) & 1u) {
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = (enc >> (4 * j)) & 3u;
           const uint32_t c = (i == 0) ? ch.x : ((i == 1) ? ch.y : ((i == 2) ? ch.z : ch.w));
           s_stack[sp][tid] = c;
-          sp++;
+          sp += (int)((hitmask >> i) & 1u);
         }
-      }
-      if (sp == 0) {
-        cur = kSentinel;
-      } else {
-        sp--;
-        cur = s_stack[sp][tid];
+        if (sp == 0) {
+          cur = kSentinel;
+        } else {
+          sp--;
+          cur = s_stack[sp][tid];
+        }
       }
     }
 
     // =============== phase C: one leaf (qbvh.rs:413-490) ========================================
-    if (cur != kSentinel) {
+    if (cur >= 0x80000000u) {
       const uint32_t count = (cur >> 27) & 0xFu;
       const uint32_t first = cur & 0x7FFFFFFu;
       if (COUNT) n_tris += count;

@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -21,8 +22,8 @@ namespace yart {
 // ---------------------------------------------------------------------------------------------
 // export of one finished ray for yart_closest_hit
 // ---------------------------------------------------------------------------------------------
-__device__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim, double bu,
-                           double bv) {
+__device__ __noinline__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim,
+                                        double bu, double bv) {
   yart_hit out;
   if (obj == YART_MISS) {
     out.t = d_inf(); out.u = 0.0; out.v = 0.0; out.prim_id = YART_MISS; out.obj_id = YART_MISS; out.front_face = 0;
@@ -306,7 +307,15 @@ TraceKernel pick_trace_kernel(bool near, bool count, uint32_t max_stack) {
   return count ? k_trace<false, true, 64> : k_trace<false, false, 64>;
 }
 
-int launch_trace(yart_ctx* ctx, const TraceParams& P, bool near, bool count) {
+int tune_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+int launch_trace(yart_ctx* ctx, TraceParams P, bool near, bool count) {
+  static const int rt = tune_env("YART_TUNE_RT", 8), nt = tune_env("YART_TUNE_NT", 12);
+  P.refill_threshold = (uint32_t)std::max(1, std::min(32, rt));
+  P.node_threshold = (uint32_t)std::max(1, std::min(32, nt));
   TraceKernel k = pick_trace_kernel(near, count, ctx->max_stack);
   int grid = 0;
   int rc = grid_for(ctx, reinterpret_cast<const void*>(k), kTraceThreads, &grid);
@@ -728,7 +737,10 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
     uint32_t* work = ctx->work.as<uint32_t>();
     std::vector<uint32_t> h_counts(n_counts);
     const bool near = o->order == YART_ORDER_NEAR;
+    const bool count = (o->flags & YART_FLAG_COUNT_VISITS) != 0;
     const int stream_grid = ctx->sm_count * 8;
+    CUDA_TRY(ctx, ctx->counters.reserve(64));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
 
     for (uint32_t s0 = o->sample_begin; s0 < o->sample_end; s0 += spp_batch) {
       const uint32_t spp = std::min(spp_batch, o->sample_end - s0);
@@ -757,6 +769,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
           P.n_items_dev = counts + b;
           P.work_counter = work + b;
           P.hits = R.st.hits;
+          P.counters = ctx->counters.as<unsigned long long>();
           P.t_min = 0.001; // world.hit(ray_in, 0.001, f64::INFINITY) (main.rs:548)
           P.t_max = INFINITY;
           P.seed = o->seed;
@@ -765,7 +778,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
           P.sample_base = s0;
           P.pixel_base = p0;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1)], ctx->stream));
-          rc = launch_trace(ctx, P, near, false);
+          rc = launch_trace(ctx, P, near, count);
           if (rc) return rc;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1) + 1], ctx->stream));
           k_shade<<<stream_grid, 256, 0, ctx->stream>>>(R, qa, counts + b, qb, counts + b + 1, b);
@@ -797,11 +810,16 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
     }
   }
   if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(film_xyz, d_film, film_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long visit[2] = {0, 0};
+  if ((o->flags & YART_FLAG_COUNT_VISITS) && n_samples > 0)
+    CUDA_TRY(ctx, cudaMemcpyAsync(visit, ctx->counters.p, sizeof(visit), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (stats) {
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    stats->node_visits = visit[0];
+    stats->tri_tests = visit[1];
     stats->rays = total_rays;
     stats->paths = total_paths;
     stats->kernel_launches = launches;
