@@ -109,8 +109,8 @@ HIT_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim_id", "<u4
 assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 40
 
 # the flat QBVH layout (csrc/host_common.h)
-NODE_DTYPE = np.dtype([("min_x", "<f4", 4), ("min_y", "<f4", 4), ("min_z", "<f4", 4), ("max_x", "<f4", 4),
-                       ("max_y", "<f4", 4), ("max_z", "<f4", 4), ("child", "<u4", 4), ("axes", "<u4"),
+NODE_DTYPE = np.dtype([("min_x", "<f4", 4), ("max_x", "<f4", 4), ("min_y", "<f4", 4), ("max_y", "<f4", 4),
+                       ("min_z", "<f4", 4), ("max_z", "<f4", 4), ("child", "<u4", 4), ("axes", "<u4"),
                        ("pad", "<u4", 3)])
 TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("orig", "<u4"), ("v1", "<f4", 3), ("pad1", "<u4"), ("v2", "<f4", 3),
                       ("pad2", "<u4")])

@@ -92,11 +92,25 @@ YART_DEV D3 random_in_unit_sphere(const Rng& rng, uint32_t bounce) {
   return d3(0.0, 0.0, 0.0);
 }
 
+// 256-bit read-only global load (LDG.E.256 on sm_100): one instruction and one L1 wavefront per
+// 32-byte sector instead of two 128-bit loads
+struct F8 {
+  float4 lo, hi;
+};
+YART_DEV F8 ldg256(const float4* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
+                 "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Scene in HBM
 // ---------------------------------------------------------------------------------------------
 struct DevMesh {
-  const float4* nodes;  // 8 float4 per node (host_common.h FlatNode)
+  const float4* nodes;  // 8 float4 per node (host_common.h FlatNode: x, y, z slab pairs, children)
   const float4* tris;   // 3 float4 per triangle, tree order (FlatTri)
   const double* shade;  // 12 doubles per triangle (FlatTriShade: 9 normals + 6 float uvs)
   uint32_t root;

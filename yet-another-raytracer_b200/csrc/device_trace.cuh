@@ -169,8 +169,8 @@ YART_DEV bool group_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
       }
     } else {
       const float4* nd = g.nodes + (size_t)id * 8;
-      const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 1), mnz = __ldg(nd + 2);
-      const float4 mxx = __ldg(nd + 3), mxy = __ldg(nd + 4), mxz = __ldg(nd + 5);
+      const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 2), mnz = __ldg(nd + 4);
+      const float4 mxx = __ldg(nd + 1), mxy = __ldg(nd + 3), mxz = __ldg(nd + 5);
       const uint4 ch = __ldg(reinterpret_cast<const uint4*>(nd + 6));
       const float lo[4][3] = {{mnx.x, mny.x, mnz.x}, {mnx.y, mny.y, mnz.y}, {mnx.z, mny.z, mnz.z}, {mnx.w, mny.w, mnz.w}};
       const float hi[4][3] = {{mxx.x, mxy.x, mxz.x}, {mxx.y, mxy.y, mxz.y}, {mxx.z, mxy.z, mxz.z}, {mxx.w, mxy.w, mxz.w}};
@@ -287,8 +287,8 @@ YART_DEV double max_nn(double a, double b) { return a > b ? a : b; }
 template <bool NEAR>
 __device__ __noinline__ uint32_t box4_ieee(const float4* nd, double ox, double oy, double oz, double ix, double iy,
                                            double iz, double t_min, double t_best) {
-  const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 1), mnz = __ldg(nd + 2);
-  const float4 mxx = __ldg(nd + 3), mxy = __ldg(nd + 4), mxz = __ldg(nd + 5);
+  const float4 mnx = __ldg(nd + 0), mny = __ldg(nd + 2), mnz = __ldg(nd + 4);
+  const float4 mxx = __ldg(nd + 1), mxy = __ldg(nd + 3), mxz = __ldg(nd + 5);
   uint32_t hitmask = 0;
 #define YART_BOX(K, LX, LY, LZ, HX, HY, HZ)                                        \
   {                                                                                \
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
   int sp = 0;
   double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0; // ray in the mesh's space
   uint32_t sgn = 0;            // ORDER_TABLE sign bits (mirrored when NEAR)
-  uint32_t near_x = 0, near_y = 1, near_z = 2; // float4 index of the plane the ray enters first, per axis
+  uint32_t pos = 0;            // bit a set: direction component a is >= 0 (qbvh.rs:388-392)
   bool weird = false;          // a zero / non-finite component: slabs can be NaN, take the IEEE path
   const float4* nodes = nullptr;
   const float4* tris = nullptr;
@@ -380,11 +380,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
             ox = ro.x; oy = ro.y; oz = ro.z;
             dx = rd.x; dy = rd.y; dz = rd.z;
             ix = 1.0 / dx; iy = 1.0 / dy; iz = 1.0 / dz; // qbvh.rs:403-407
-            const uint32_t pos = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
+            pos = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
             sgn = NEAR ? (pos ^ 7u) : pos;
-            near_x = (pos & 1u) ? 0u : 3u;
-            near_y = (pos & 2u) ? 1u : 4u;
-            near_z = (pos & 4u) ? 2u : 5u;
             // (b - o) * (1/d) can only be NaN when 1/d is infinite or the ray itself is not finite
             weird = !(isfinite(ix) && isfinite(iy) && isfinite(iz) && isfinite(ox) && isfinite(oy) && isfinite(oz));
             cur = m.root;
@@ -429,16 +426,23 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
       }
       if (has_node) {
         const float4* nd = nodes + (size_t)cur * 8;
-        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(nd + 6));
-        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(nd + 7));
+        // the whole 128-byte node in four 256-bit loads, all in flight together
+        const F8 sx8 = ldg256(nd + 0), sy8 = ldg256(nd + 2), sz8 = ldg256(nd + 4), cm8 = ldg256(nd + 6);
+        const uint4 ch = make_uint4(__float_as_uint(cm8.lo.x), __float_as_uint(cm8.lo.y), __float_as_uint(cm8.lo.z),
+                                    __float_as_uint(cm8.lo.w));
+        const uint32_t axes = __float_as_uint(cm8.hi.x);
         if (COUNT) n_nodes++;
         uint32_t hitmask = 0;
         if (!weird) {
           // Fast path.  All slab values are finite or +-inf, never NaN, and b_min <= b_max, so
           // min(t0,t1) is the plane on the side the ray comes from and max(t0,t1) the other one:
           // identical values to qbvh.rs:495-519 with half the min/max work and no NaN handling.
-          const float4 nx = __ldg(nd + near_x), ny = __ldg(nd + near_y), nz = __ldg(nd + near_z);
-          const float4 fx = __ldg(nd + (3u - near_x)), fy = __ldg(nd + (5u - near_y)), fz = __ldg(nd + (7u - near_z));
+          const bool px = (pos & 1u) != 0, py = (pos & 2u) != 0, pz = (pos & 4u) != 0;
+#define YART_SEL4(P_, A, B) make_float4((P_) ? A.x : B.x, (P_) ? A.y : B.y, (P_) ? A.z : B.z, (P_) ? A.w : B.w)
+          const float4 nx = YART_SEL4(px, sx8.lo, sx8.hi), fx = YART_SEL4(px, sx8.hi, sx8.lo);
+          const float4 ny = YART_SEL4(py, sy8.lo, sy8.hi), fy = YART_SEL4(py, sy8.hi, sy8.lo);
+          const float4 nz = YART_SEL4(pz, sz8.lo, sz8.hi), fz = YART_SEL4(pz, sz8.hi, sz8.lo);
+#undef YART_SEL4
 #define YART_BOX_FAST(K, C)                                                                              \
   {                                                                                                      \
     double tn = max_nn(P.t_min, ((double)nx.C - ox) * ix);                                               \
@@ -467,8 +471,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t i = (enc >> (4 * j)) & 3u;
-          const uint32_t c = (i == 0) ? ch.x : ((i == 1) ? ch.y : ((i == 2) ? ch.z : ch.w));
-          s_stack[sp][tid] = c;
+          const uint32_t c01 = (i & 1u) ? ch.y : ch.x, c23 = (i & 1u) ? ch.w : ch.z;
+          s_stack[sp][tid] = (i & 2u) ? c23 : c01;
           sp += (int)((hitmask >> i) & 1u);
         }
         if (sp == 0) {

@@ -33,10 +33,13 @@ struct TriSoup {
 bool load_obj(const std::string& path, TriSoup& out, std::string& err);
 
 // ---- flattened L4QBVH: the device layout (DESIGN.md "Data layout in HBM") -------------------
-// Node: 128 bytes = one L2 line.  lane k of every float[4] is child k (LL, LR, RL, RR).
+// Node: 128 bytes = one L2 line = four 32-byte sectors, each fetched with one 256-bit load
+// (LDG.E.256): {min_x,max_x} {min_y,max_y} {min_z,max_z} {children,axes}.  Lane k of every float[4]
+// is child k (LL, LR, RL, RR).
 struct alignas(128) FlatNode {
-  float min_x[4], min_y[4], min_z[4];
-  float max_x[4], max_y[4], max_z[4];
+  float min_x[4], max_x[4];
+  float min_y[4], max_y[4];
+  float min_z[4], max_z[4];
   uint32_t child[4]; // bit31 leaf | count<<27 | first triangle (tree order);  inner: node index;
                      // 0xFFFFFFFF = absent (its box is +FLT_MAX, never hit)
   uint32_t axes;     // top | left<<2 | right<<4   (QBVHNode.top_axis/left_axis/right_axis)

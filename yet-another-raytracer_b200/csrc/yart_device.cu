@@ -320,6 +320,9 @@ int launch_trace(yart_ctx* ctx, TraceParams P, bool near, bool count) {
   int grid = 0;
   int rc = grid_for(ctx, reinterpret_cast<const void*>(k), kTraceThreads, &grid);
   if (rc) return rc;
+  // leave everything the stacks do not need to L1: the tree's upper levels live there
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributePreferredSharedMemoryCarveout,
+                       tune_env("YART_TUNE_CARVEOUT", 35));
   k<<<grid, kTraceThreads, 0, ctx->stream>>>(P);
   CUDA_TRY(ctx, cudaGetLastError());
   return YART_OK;
