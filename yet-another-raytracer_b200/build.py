@@ -32,6 +32,8 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "--shared", "-cudart", "shared",
 ]
+if os.environ.get("YART_TRAVERSE_MIN_BLOCKS"):  # tuning knob: resident blocks per SM the kernel is compiled for
+    NVCC_FLAGS += ["-DYART_TRAVERSE_MIN_BLOCKS=" + os.environ["YART_TRAVERSE_MIN_BLOCKS"]]
 
 
 def _digest():

@@ -1,11 +1,13 @@
 // device_trace.cuh -- closest-hit: the persistent-thread QBVH traversal kernel and the analytic
 // primitives around it.
 //
-// One lane = one ray.  A lane is a small state machine that walks the world's object list in
-// order (HittableList::hit, reference hittable.rs:66-79): analytic objects are intersected in
-// place, a TriangleMesh object switches the lane into QBVH traversal (L4QBVH::hit,
-// qbvh.rs:381-543) with the ray moved into the instance's space (Translate / RotateY,
-// hittable.rs:136-152, 217-251).  Lanes that run out of work fetch the next ray from a global
+// HittableList::hit (reference hittable.rs:66-79) walks the world's object list in order with a
+// shrinking [t_min, closest] interval.  Here the list is cut into PASSES, run in list order over
+// the whole ray queue, each pass reading and updating the per-ray closest hit in HBM:
+//   * a TriangleMesh object = one launch of k_traverse: L4QBVH::hit (qbvh.rs:381-543) with the
+//     rays moved into the instance's space (Translate / RotateY, hittable.rs:136-152, 217-251);
+//   * a run of consecutive analytic objects = one launch of k_analytic (one thread per ray).
+// k_traverse is persistent: one lane = one ray; lanes that finish fetch the next ray from a global
 // counter (warp-aggregated), so a warp stays full while rays of very different cost retire.
 // The traversal stack lives in shared memory, one column per lane (no bank conflicts).
 #pragma once
@@ -229,52 +231,48 @@ YART_DEV bool object_hit_t(const DevScene& S, const yart_object& o, uint32_t obj
 }
 
 // ---------------------------------------------------------------------------------------------
-// the traversal kernel
+// pass parameters
 // ---------------------------------------------------------------------------------------------
-struct TraceParams {
-  DevScene scene;
-  const yart_object* objects; // the list to walk: the world, or a 1-entry list for a mesh-only query
-  uint32_t n_objects;
-  uint32_t media_mask;        // 1 if any object carries YART_WRAP_MEDIUM (needs the Philox stream)
-  const yart_ray* rays;       // indexed by ray id
-  const double* ray_time;     // indexed by ray id, may be null (time 0)
-  const uint32_t* queue;      // work item -> ray id, null = identity
+struct PassCommon {
+  const yart_ray* rays;        // indexed by ray id
+  const uint32_t* queue;       // work item -> ray id, null = identity
   const uint32_t* n_items_dev; // number of work items in device memory, null = use n_items
   uint64_t n_items;
-  uint32_t* work_counter;     // zero before launch
-  DevHit* hits;               // indexed by ray id          (renderer)
-  yart_hit* hits_export;      // indexed by ray id, or null (yart_closest_hit)
-  unsigned long long* counters; // [0] node visits, [1] triangle tests (COUNT only)
+  DevHit* hits;                // indexed by ray id: the closest hit so far
+  uint32_t first_pass;         // 1: nothing recorded yet, start from t_max and always write
+  uint32_t _pad;
   double t_min, t_max;
-  uint64_t seed;              // Philox key for media inside world.hit
-  uint32_t bounce;
-  uint32_t spp_batch;         // ray id -> (pixel, sample) = (id / spp_batch, sample_base + id % spp_batch)
-  uint32_t sample_base;
-  uint32_t pixel_base;
-  uint32_t refill_threshold;  // run the fetch/advance phase once this many lanes wait for it
-  uint32_t node_threshold;    // leave the inner-node loop once fewer lanes than this are in it
 };
 
-// finalise one ray for yart_closest_hit: original triangle id and front_face as the reference's
-// HitRecord would carry them (qbvh.rs:452-489, triangle.rs:80-91 etc.)
-__device__ __noinline__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim,
-                                        double bu, double bv);
+struct TraverseParams {
+  PassCommon c;
+  const float4* nodes;
+  const float4* tris;
+  uint32_t root;
+  uint32_t obj_index;         // world object index recorded with a hit
+  uint32_t wrap;              // YART_WRAP_ROTATE_Y / TRANSLATE of this instance
+  uint32_t refill_threshold;  // run the retire/fetch phase once this many lanes wait for it
+  uint32_t node_threshold;    // leave the inner-node loop once fewer lanes than this are in it
+  uint32_t _pad;
+  double sin_theta, cos_theta, offset[3];
+  uint32_t* work_counter;     // zero before launch
+  unsigned long long* counters; // [0] node visits, [1] triangle tests (COUNT only)
+};
 
-// every non-mesh object of the list, out of line: keeps spheres / boxes / media / groups and their
-// registers out of the traversal loop
-__device__ __noinline__ bool object_hit_outlined(const TraceParams& P, const yart_object& o, uint32_t oi, uint32_t ray_id,
-                                                 D3 wo, D3 wd, double t_best, double& t, uint32_t& prim, double& bu,
-                                                 double& bv) {
-  Rng rng;
-  if (P.media_mask) {
-    const uint32_t pix = P.pixel_base + ray_id / P.spp_batch, smp = P.sample_base + ray_id % P.spp_batch;
-    rng = make_rng(P.seed, pix, smp);
-  } else {
-    rng = make_rng(0, 0, 0);
-  }
-  const double time = P.ray_time ? P.ray_time[ray_id] : 0.0;
-  return object_hit_t(P.scene, o, oi, wo, wd, time, P.t_min, t_best, rng, P.bounce, t, prim, bu, bv);
-}
+struct AnalyticParams {
+  PassCommon c;
+  DevScene scene;
+  const yart_object* objects; // the world list
+  uint32_t obj_begin, obj_end;
+  const double* ray_time;     // indexed by ray id, may be null (time 0)
+  uint64_t seed;              // Philox key for media inside world.hit
+  uint32_t bounce;
+  uint32_t spp_batch;         // ray id -> (pixel, sample) = (pixel_base + id / spp_batch, sample_base + id % spp_batch)
+  uint32_t sample_base;
+  uint32_t pixel_base;
+  uint32_t media_mask;
+  uint32_t _pad;
+};
 
 // min / max for values that cannot be NaN: one DSETP + selects instead of the IEEE minNum/maxNum
 // sequence (DSETP.MIN + SEL + FSEL + NaN quieting) the compiler emits for fmin/fmax on doubles
@@ -310,104 +308,96 @@ __device__ __noinline__ uint32_t box4_ieee(const float4* nd, double ox, double o
   return hitmask;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_traverse: one TriangleMesh instance against the whole ray queue
+// ---------------------------------------------------------------------------------------------
+#ifndef YART_TRAVERSE_MIN_BLOCKS
+#define YART_TRAVERSE_MIN_BLOCKS 4
+#endif
+
 template <bool NEAR, bool COUNT, int STACK>
-__global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P) {
+__global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_traverse(const TraverseParams P) {
   __shared__ uint32_t s_stack[STACK + 1][kTraceThreads];
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31;
-  const uint64_t n_items = P.n_items_dev ? (uint64_t)*P.n_items_dev : P.n_items;
+  const uint64_t n_items = P.c.n_items_dev ? (uint64_t)*P.c.n_items_dev : P.c.n_items;
   const uint32_t RT = P.refill_threshold, NT = P.node_threshold;
+  const float4* __restrict__ nodes = P.nodes;
+  const float4* __restrict__ tris = P.tris;
+  const double t_min = P.c.t_min;
 
   // ---- lane state ----
   uint32_t ray_id = YART_MISS; // YART_MISS = idle
-  uint32_t next_obj = 0;       // next object of the list to start
   uint32_t cur = kSentinel;    // current stack top (node or leaf id), kSentinel = not traversing
   int sp = 0;
   double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0; // ray in the mesh's space
-  uint32_t sgn = 0;            // ORDER_TABLE sign bits (mirrored when NEAR)
-  uint32_t pos = 0;            // bit a set: direction component a is >= 0 (qbvh.rs:388-392)
-  bool weird = false;          // a zero / non-finite component: slabs can be NaN, take the IEEE path
-  const float4* nodes = nullptr;
-  const float4* tris = nullptr;
+  uint32_t sgn = 0;  // ORDER_TABLE sign bits (mirrored when NEAR)
+  uint32_t pos = 0;  // bit a set: direction component a is >= 0 (qbvh.rs:388-392); bit 3: `weird`
   double t_best = 0, t_entry = 0, best_bu = 0, best_bv = 0;
-  uint32_t best_obj = YART_MISS, best_prim = 0, cur_obj = 0;
-  bool exhausted = false; // the global queue is empty
+  uint32_t best_prim = YART_MISS; // YART_MISS = this mesh has not produced a hit
+  bool exhausted = false;         // the global queue is empty
   unsigned long long n_nodes = 0, n_tris = 0;
 
   for (;;) {
-    // =============== phase A: advance through the object list / retire / fetch =================
-    // Batched: lanes that finished a traversal wait until RT of them can run this (long, divergent)
-    // code together, unless nobody else has work.
+    // =============== phase A: retire finished rays, fetch new ones ================================
+    // Batched: lanes that finished wait until RT of them can run this together, unless nobody else has work.
     const bool want_a = (cur == kSentinel) && !(exhausted && ray_id == YART_MISS);
     const uint32_t a_mask = __ballot_sync(0xffffffffu, want_a);
     const uint32_t busy_mask = __ballot_sync(0xffffffffu, cur != kSentinel);
     if (want_a && ((uint32_t)__popc(a_mask) >= RT || busy_mask == 0)) {
-      for (;;) {
-        if (ray_id == YART_MISS) {
-          if (exhausted) break;
-          const uint32_t mask = __activemask();
-          const int leader = __ffs(mask) - 1;
-          const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-          uint32_t base = 0;
-          if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(mask));
-          base = __shfl_sync(mask, base, leader);
-          const uint64_t item = (uint64_t)base + rank;
-          if (item >= n_items) {
-            exhausted = true;
-            break;
-          }
-          ray_id = P.queue ? P.queue[item] : (uint32_t)item;
-          next_obj = 0;
-          t_best = P.t_max;
-          best_obj = YART_MISS;
-          best_prim = 0;
-          best_bu = best_bv = 0.0;
-        }
-        // walk the list until a mesh needs traversal or the list ends
-        bool started = false;
-        const yart_ray wr = P.rays[ray_id];
-        const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
-        const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
-        while (next_obj < P.n_objects) {
-          const yart_object& o = P.objects[next_obj];
-          const uint32_t oi = next_obj++;
-          if (o.kind == YART_OBJ_MESH && !(o.wrap & YART_WRAP_MEDIUM)) {
-            D3 ro = wo, rd = wd;
-            to_object_space(o, ro, rd);
-            const DevMesh m = P.scene.meshes[o.index];
-            nodes = m.nodes;
-            tris = m.tris;
-            ox = ro.x; oy = ro.y; oz = ro.z;
-            dx = rd.x; dy = rd.y; dz = rd.z;
-            ix = 1.0 / dx; iy = 1.0 / dy; iz = 1.0 / dz; // qbvh.rs:403-407
-            pos = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
-            sgn = NEAR ? (pos ^ 7u) : pos;
-            // (b - o) * (1/d) can only be NaN when 1/d is infinite or the ray itself is not finite
-            weird = !(isfinite(ix) && isfinite(iy) && isfinite(iz) && isfinite(ox) && isfinite(oy) && isfinite(oz));
-            cur = m.root;
-            sp = 0;
-            cur_obj = oi;
-            t_entry = t_best;
-            started = true;
-            break;
-          }
-          double t, bu, bv;
-          uint32_t prim;
-          if (object_hit_outlined(P, o, oi, ray_id, wo, wd, t_best, t, prim, bu, bv)) {
-            t_best = t; best_obj = oi; best_prim = prim; best_bu = bu; best_bv = bv;
-          }
-        }
-        if (started) break;
-        // list finished: retire this ray
-        if (P.hits_export) {
-          export_hit(P, ray_id, t_best, best_obj, best_prim, best_bu, best_bv);
-        } else {
+      if (ray_id != YART_MISS) { // retire: record the hit if this mesh improved on the earlier objects
+        if (best_prim != YART_MISS) {
           DevHit h;
-          h.t = (best_obj == YART_MISS) ? d_inf() : t_best;
-          h.bu = best_bu; h.bv = best_bv; h.obj = best_obj; h.prim = best_prim;
-          P.hits[ray_id] = h;
+          h.t = t_best; h.bu = best_bu; h.bv = best_bv; h.obj = P.obj_index; h.prim = best_prim;
+          P.c.hits[ray_id] = h;
+        } else if (P.c.first_pass) {
+          DevHit h;
+          h.t = d_inf(); h.bu = 0.0; h.bv = 0.0; h.obj = YART_MISS; h.prim = 0;
+          P.c.hits[ray_id] = h;
         }
         ray_id = YART_MISS;
+      }
+      const uint32_t fmask = __ballot_sync(a_mask, !exhausted);
+      if (!exhausted) { // fetch: one atomic for all fetching lanes of the warp
+        const int leader = __ffs(fmask) - 1;
+        const uint32_t rank = __popc(fmask & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(fmask));
+        base = __shfl_sync(fmask, base, leader);
+        const uint64_t item = (uint64_t)base + rank;
+        if (item >= n_items) {
+          exhausted = true;
+        } else {
+          ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
+          const yart_ray wr = P.c.rays[ray_id];
+          t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
+          D3 ro = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
+          D3 rd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+          // ray into the instance's space (hittable.rs:137-143, 218-227); uniform across the launch
+          if (P.wrap & YART_WRAP_TRANSLATE) ro = ro - d3(P.offset[0], P.offset[1], P.offset[2]);
+          if (P.wrap & YART_WRAP_ROTATE_Y) {
+            const double ct = P.cos_theta, st = P.sin_theta;
+            D3 org = ro, dir = rd;
+            org.x = ct * ro.x - st * ro.z;
+            org.z = st * ro.x + ct * ro.z;
+            dir.x = ct * rd.x - st * rd.z;
+            dir.z = st * rd.x + ct * rd.z;
+            ro = org;
+            rd = dir;
+          }
+          ox = ro.x; oy = ro.y; oz = ro.z;
+          dx = rd.x; dy = rd.y; dz = rd.z;
+          ix = 1.0 / dx; iy = 1.0 / dy; iz = 1.0 / dz; // qbvh.rs:403-407
+          pos = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
+          sgn = NEAR ? (pos ^ 7u) : pos;
+          // (b - o) * (1/d) can only be NaN when 1/d is infinite or the ray itself is not finite
+          if (!(isfinite(ix) && isfinite(iy) && isfinite(iz) && isfinite(ox) && isfinite(oy) && isfinite(oz))) pos |= 8u;
+          cur = P.root;
+          sp = 0;
+          t_entry = t_best;
+          best_prim = YART_MISS;
+          best_bu = best_bv = 0.0;
+        }
       }
     }
     if (!__any_sync(0xffffffffu, ray_id != YART_MISS)) break;
@@ -433,7 +423,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
         const uint32_t axes = __float_as_uint(cm8.hi.x);
         if (COUNT) n_nodes++;
         uint32_t hitmask = 0;
-        if (!weird) {
+        if (!(pos & 8u)) {
           // Fast path.  All slab values are finite or +-inf, never NaN, and b_min <= b_max, so
           // min(t0,t1) is the plane on the side the ray comes from and max(t0,t1) the other one:
           // identical values to qbvh.rs:495-519 with half the min/max work and no NaN handling.
@@ -445,7 +435,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
 #undef YART_SEL4
 #define YART_BOX_FAST(K, C)                                                                              \
   {                                                                                                      \
-    double tn = max_nn(P.t_min, ((double)nx.C - ox) * ix);                                               \
+    double tn = max_nn(t_min, ((double)nx.C - ox) * ix);                                                 \
     tn = max_nn(tn, ((double)ny.C - oy) * iy);                                                           \
     tn = max_nn(tn, ((double)nz.C - oz) * iz);                                                           \
     double tf = NEAR ? ((double)fx.C - ox) * ix : min_nn(t_best, ((double)fx.C - ox) * ix);             \
@@ -460,7 +450,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
           YART_BOX_FAST(3, w)
 #undef YART_BOX_FAST
         } else {
-          hitmask = box4_ieee<NEAR>(nd, ox, oy, oz, ix, iy, iz, P.t_min, t_best);
+          hitmask = box4_ieee<NEAR>(nd, ox, oy, oz, ix, iy, iz, t_min, t_best);
         }
         // ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]] (qbvh.rs:521-524)
         const uint32_t idx = (((sgn >> (axes & 3u)) & 1u) << 2) | (((sgn >> ((axes >> 2) & 3u)) & 1u) << 1) |
@@ -507,12 +497,12 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
         const double v = f * (dx * qx + dy * qy + dz * qz);
         ok = ok && (v >= 0.0) && ((u + v) <= 1.0);
         const double t = f * (e2x * qx + e2y * qy + e2z * qz);
-        ok = ok && (t >= P.t_min);
+        ok = ok && (t >= t_min);
         // REFERENCE: first found wins (`t_max > t`, qbvh.rs:478).  NEAR: mirrored -- last found wins
         // among this mesh's equal-t hits, still strictly closer than what earlier objects left.
         ok = ok && (NEAR ? ((t <= t_best) && (t < t_entry)) : (t_best > t));
         if (ok) {
-          t_best = t; best_obj = cur_obj; best_prim = first + i; best_bu = u; best_bv = v;
+          t_best = t; best_prim = first + i; best_bu = u; best_bv = v;
         }
       }
       if (sp == 0) {
@@ -526,6 +516,46 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(const TraceParams P)
   if (COUNT) {
     atomicAdd(&P.counters[0], n_nodes);
     atomicAdd(&P.counters[1], n_tris);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_analytic: a run of consecutive non-mesh objects of the list, one thread per queued ray
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_analytic(const AnalyticParams P) {
+  const uint64_t n = P.c.n_items_dev ? (uint64_t)*P.c.n_items_dev : P.c.n_items;
+  for (uint64_t item = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; item < n; item += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
+    const yart_ray wr = P.c.rays[ray_id];
+    const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
+    const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+    DevHit h;
+    if (P.c.first_pass) {
+      h.t = d_inf(); h.bu = 0.0; h.bv = 0.0; h.obj = YART_MISS; h.prim = 0;
+    } else {
+      h = P.c.hits[ray_id];
+    }
+    double t_best = fmin(h.t, P.c.t_max);
+    bool changed = P.c.first_pass != 0;
+    Rng rng;
+    if (P.media_mask) rng = make_rng(P.seed, P.pixel_base + ray_id / P.spp_batch, P.sample_base + ray_id % P.spp_batch);
+    else rng = make_rng(0, 0, 0);
+    const double time = P.ray_time ? P.ray_time[ray_id] : 0.0;
+    for (uint32_t oi = P.obj_begin; oi < P.obj_end; ++oi) {
+      const yart_object& o = P.objects[oi];
+      double t, bu = 0.0, bv = 0.0;
+      uint32_t prim = 0;
+      bool hit;
+      if (o.kind == YART_OBJ_SPHERE && o.wrap == 0)
+        hit = sphere_t(d3(o.p[0], o.p[1], o.p[2]), o.p[3], wo, wd, P.c.t_min, t_best, t);
+      else
+        hit = object_hit_t(P.scene, o, oi, wo, wd, time, P.c.t_min, t_best, rng, P.bounce, t, prim, bu, bv);
+      if (hit) {
+        t_best = t; h.t = t; h.obj = oi; h.prim = prim; h.bu = bu; h.bv = bv;
+        changed = true;
+      }
+    }
+    if (changed) P.c.hits[ray_id] = h;
   }
 }
 

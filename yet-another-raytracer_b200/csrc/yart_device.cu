@@ -20,40 +20,39 @@
 namespace yart {
 
 // ---------------------------------------------------------------------------------------------
-// export of one finished ray for yart_closest_hit
+// k_export: DevHit -> yart_hit for yart_closest_hit: original triangle id and front_face as the
+// reference's HitRecord would carry them (qbvh.rs:452-489, triangle.rs:80-91 etc.)
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void export_hit(const TraceParams& P, uint32_t ray_id, double t, uint32_t obj, uint32_t prim,
-                                        double bu, double bv) {
-  yart_hit out;
-  if (obj == YART_MISS) {
-    out.t = d_inf(); out.u = 0.0; out.v = 0.0; out.prim_id = YART_MISS; out.obj_id = YART_MISS; out.front_face = 0;
-    out._pad = 0;
-    P.hits_export[ray_id] = out;
-    return;
+__global__ void __launch_bounds__(256) k_export(const DevScene S, const yart_ray* rays, const DevHit* hits, yart_hit* out_hits,
+                                                 uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const DevHit h = hits[i];
+    yart_hit out;
+    if (h.obj == YART_MISS) {
+      out.t = d_inf(); out.u = 0.0; out.v = 0.0; out.prim_id = YART_MISS; out.obj_id = YART_MISS; out.front_face = 0;
+      out._pad = 0;
+      out_hits[i] = out;
+      continue;
+    }
+    const yart_ray wr = rays[i];
+    const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
+    const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+    const yart_object& o = S.objects[h.obj];
+    HitRec rec; // rebuild the HitRecord of this object to get front_face exactly as the reference computes it
+    world_record(S, h, wo, wd, 0.0, rec);
+    out.t = h.t; out.u = h.bu; out.v = h.bv; out.obj_id = h.obj; out.front_face = rec.front_face ? 1u : 0u; out._pad = 0;
+    if (o.wrap & YART_WRAP_MEDIUM) {
+      out.prim_id = 0;
+    } else if (o.kind == YART_OBJ_MESH) {
+      const DevMesh m = S.meshes[o.index];
+      out.prim_id = __float_as_uint(__ldg(m.tris + (size_t)h.prim * 3).w); // FlatTri.orig
+    } else if (o.kind == YART_OBJ_GROUP) {
+      out.prim_id = S.groups[o.index].member_orig[h.prim >> 3];
+    } else {
+      out.prim_id = h.prim;
+    }
+    out_hits[i] = out;
   }
-  const yart_ray wr = P.rays[ray_id];
-  const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
-  const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
-  const yart_object& o = P.objects[obj];
-  // rebuild the HitRecord of this object to get front_face exactly as the reference computes it
-  DevScene S = P.scene;
-  S.objects = P.objects;
-  DevHit h;
-  h.t = t; h.bu = bu; h.bv = bv; h.obj = obj; h.prim = prim;
-  HitRec rec;
-  world_record(S, h, wo, wd, P.ray_time ? P.ray_time[ray_id] : 0.0, rec);
-  out.t = t; out.u = bu; out.v = bv; out.obj_id = obj; out.front_face = rec.front_face ? 1u : 0u; out._pad = 0;
-  if (o.wrap & YART_WRAP_MEDIUM) {
-    out.prim_id = 0;
-  } else if (o.kind == YART_OBJ_MESH) {
-    const DevMesh m = P.scene.meshes[o.index];
-    out.prim_id = __float_as_uint(__ldg(m.tris + (size_t)prim * 3).w); // FlatTri.orig
-  } else if (o.kind == YART_OBJ_GROUP) {
-    out.prim_id = P.scene.groups[o.index].member_orig[prim >> 3];
-  } else {
-    out.prim_id = prim;
-  }
-  P.hits_export[ray_id] = out;
 }
 
 namespace {
@@ -216,6 +215,8 @@ struct yart_ctx {
   std::vector<void*> scene_allocs;
   DevScene scene;
   yart_object* d_solo = nullptr; // one un-wrapped MESH object per mesh, for mesh-only queries
+  std::vector<yart_object> h_objects; // host copy of the world list: the pass plan is made on the host
+  std::vector<DevMesh> h_meshes;
   uint32_t n_meshes = 0;
   uint32_t max_stack = 0;
   bool has_media = false;
@@ -297,14 +298,14 @@ int grid_for(yart_ctx* ctx, const void* kernel, int threads, int* grid) {
   return YART_OK;
 }
 
-typedef void (*TraceKernel)(const TraceParams);
-TraceKernel pick_trace_kernel(bool near, bool count, uint32_t max_stack) {
+typedef void (*TraverseKernel)(const TraverseParams);
+TraverseKernel pick_traverse_kernel(bool near, bool count, uint32_t max_stack) {
   if (max_stack <= 32) {
-    if (near) return count ? k_trace<true, true, 32> : k_trace<true, false, 32>;
-    return count ? k_trace<false, true, 32> : k_trace<false, false, 32>;
+    if (near) return count ? k_traverse<true, true, 32> : k_traverse<true, false, 32>;
+    return count ? k_traverse<false, true, 32> : k_traverse<false, false, 32>;
   }
-  if (near) return count ? k_trace<true, true, 64> : k_trace<true, false, 64>;
-  return count ? k_trace<false, true, 64> : k_trace<false, false, 64>;
+  if (near) return count ? k_traverse<true, true, 64> : k_traverse<true, false, 64>;
+  return count ? k_traverse<false, true, 64> : k_traverse<false, false, 64>;
 }
 
 int tune_env(const char* name, int dflt) {
@@ -312,18 +313,92 @@ int tune_env(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-int launch_trace(yart_ctx* ctx, TraceParams P, bool near, bool count) {
+// What is the same for every pass of one closest-hit query.
+struct QueryArgs {
+  PassCommon c;
+  const yart_object* d_objects; // device copy of the list the host plan walks
+  const yart_object* h_objects;
+  uint32_t n_objects;
+  const double* ray_time;
+  uint64_t seed;
+  uint32_t bounce, spp_batch, sample_base, pixel_base;
+  uint32_t* work_counters;      // one zeroed u32 per traverse pass (at least n_objects)
+  unsigned long long* counters;
+  bool near, count;
+};
+
+// HittableList::hit (hittable.rs:66-79) as passes over the ray queue, in list order: one k_traverse per
+// mesh instance, one k_analytic per run of consecutive analytic objects.
+int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
   static const int rt = tune_env("YART_TUNE_RT", 8), nt = tune_env("YART_TUNE_NT", 12);
-  P.refill_threshold = (uint32_t)std::max(1, std::min(32, rt));
-  P.node_threshold = (uint32_t)std::max(1, std::min(32, nt));
-  TraceKernel k = pick_trace_kernel(near, count, ctx->max_stack);
-  int grid = 0;
-  int rc = grid_for(ctx, reinterpret_cast<const void*>(k), kTraceThreads, &grid);
-  if (rc) return rc;
-  // leave everything the stacks do not need to L1: the tree's upper levels live there
-  cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributePreferredSharedMemoryCarveout,
-                       tune_env("YART_TUNE_CARVEOUT", 35));
-  k<<<grid, kTraceThreads, 0, ctx->stream>>>(P);
+  static const int carve = tune_env("YART_TUNE_CARVEOUT", 35);
+  bool first = true;
+  uint32_t i = 0, n_trav = 0;
+  auto is_mesh = [&](uint32_t k) {
+    return q.h_objects[k].kind == YART_OBJ_MESH && !(q.h_objects[k].wrap & YART_WRAP_MEDIUM);
+  };
+  if (q.n_objects == 0) { // an empty world: every ray misses
+    AnalyticParams A;
+    memset(&A, 0, sizeof(A));
+    A.c = q.c;
+    A.c.first_pass = 1;
+    A.scene = ctx->scene;
+    A.objects = q.d_objects;
+    A.spp_batch = 1;
+    k_analytic<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+    if (launches) (*launches)++;
+  }
+  while (i < q.n_objects) {
+    if (is_mesh(i)) {
+      const yart_object& o = q.h_objects[i];
+      const DevMesh& m = ctx->h_meshes[o.index];
+      TraverseParams T;
+      memset(&T, 0, sizeof(T));
+      T.c = q.c;
+      T.c.first_pass = first ? 1u : 0u;
+      T.nodes = m.nodes;
+      T.tris = m.tris;
+      T.root = m.root;
+      T.obj_index = i;
+      T.wrap = o.wrap & (YART_WRAP_ROTATE_Y | YART_WRAP_TRANSLATE);
+      T.refill_threshold = (uint32_t)std::max(1, std::min(32, rt));
+      T.node_threshold = (uint32_t)std::max(1, std::min(32, nt));
+      T.sin_theta = o.sin_theta;
+      T.cos_theta = o.cos_theta;
+      for (int k = 0; k < 3; ++k) T.offset[k] = o.offset[k];
+      T.work_counter = q.work_counters + n_trav++;
+      T.counters = q.counters;
+      TraverseKernel k = pick_traverse_kernel(q.near, q.count, ctx->max_stack);
+      int per_sm = 0;
+      CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(k), kTraceThreads, 0));
+      // leave everything the stacks do not need to L1: the tree's upper levels live there
+      cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      k<<<std::max(per_sm, 1) * ctx->sm_count, kTraceThreads, 0, ctx->stream>>>(T); // persistent: one resident wave
+      i++;
+    } else {
+      uint32_t j = i;
+      while (j < q.n_objects && !is_mesh(j)) ++j;
+      AnalyticParams A;
+      memset(&A, 0, sizeof(A));
+      A.c = q.c;
+      A.c.first_pass = first ? 1u : 0u;
+      A.scene = ctx->scene;
+      A.objects = q.d_objects;
+      A.obj_begin = i;
+      A.obj_end = j;
+      A.ray_time = q.ray_time;
+      A.seed = q.seed;
+      A.bounce = q.bounce;
+      A.spp_batch = q.spp_batch ? q.spp_batch : 1;
+      A.sample_base = q.sample_base;
+      A.pixel_base = q.pixel_base;
+      A.media_mask = ctx->has_media ? 1u : 0u;
+      k_analytic<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A);
+      i = j;
+    }
+    first = false;
+    if (launches) (*launches)++;
+  }
   CUDA_TRY(ctx, cudaGetLastError());
   return YART_OK;
 }
@@ -583,6 +658,8 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
   S.n_lights = d->n_lights;
   for (int k = 0; k < 3; ++k) S.background[k] = d->background_rgb[k];
   ctx->n_meshes = d->n_meshes;
+  ctx->h_objects.assign(d->objects, d->objects + d->n_objects);
+  ctx->h_meshes = meshes;
   ctx->have_scene = true;
   return YART_OK;
 }
@@ -616,36 +693,51 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
     d_rays = ctx->rays.as<yart_ray>();
     d_hits = ctx->hits_export.as<yart_hit>();
   }
-  CUDA_TRY(ctx, ctx->work.reserve(256));
+  const uint32_t n_list = (target == YART_TARGET_WORLD) ? ctx->scene.n_objects : 1u;
+  const size_t work_bytes = ((size_t)n_list + 2) * sizeof(uint32_t);
+  CUDA_TRY(ctx, ctx->work.reserve(work_bytes));
   CUDA_TRY(ctx, ctx->counters.reserve(64));
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->work.p, 0, 256, ctx->stream));
+  CUDA_TRY(ctx, ctx->hits.reserve(n * sizeof(DevHit)));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->work.p, 0, work_bytes, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
 
-  TraceParams P;
-  memset(&P, 0, sizeof(P));
-  P.scene = ctx->scene;
+  yart_object solo;
+  memset(&solo, 0, sizeof(solo));
+  solo.kind = YART_OBJ_MESH;
+  solo.cos_theta = 1.0;
+  QueryArgs q;
+  memset(&q, 0, sizeof(q));
+  q.c.rays = d_rays;
+  q.c.n_items = n;
+  q.c.hits = ctx->hits.as<DevHit>();
+  q.c.t_min = t_min;
+  q.c.t_max = t_max;
+  DevScene export_scene = ctx->scene;
   if (target == YART_TARGET_WORLD) {
-    P.objects = ctx->scene.objects;
-    P.n_objects = ctx->scene.n_objects;
-    P.media_mask = ctx->has_media ? 1u : 0u;
+    q.d_objects = ctx->scene.objects;
+    q.h_objects = ctx->h_objects.data();
+    q.n_objects = ctx->scene.n_objects;
   } else {
-    P.objects = ctx->d_solo + target;
-    P.n_objects = 1;
-    P.media_mask = 0;
+    solo.index = target;
+    q.d_objects = ctx->d_solo + target;
+    q.h_objects = &solo;
+    q.n_objects = 1;
+    export_scene.objects = ctx->d_solo + target;
   }
-  P.rays = d_rays;
-  P.n_items = n;
-  P.work_counter = ctx->work.as<uint32_t>();
-  P.hits_export = d_hits;
-  P.counters = ctx->counters.as<unsigned long long>();
-  P.t_min = t_min;
-  P.t_max = t_max;
-  P.seed = 0;
-  P.bounce = 1;
-  P.spp_batch = 1;
+  q.seed = 0;
+  q.bounce = 1;
+  q.spp_batch = 1; // media inside world.hit: Philox stream of pixel = ray index, sample 0, bounce 1
+  q.work_counters = ctx->work.as<uint32_t>();
+  q.counters = ctx->counters.as<unsigned long long>();
+  q.near = order == YART_ORDER_NEAR;
+  q.count = count;
+  uint64_t launches = 0;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = launch_trace(ctx, P, order == YART_ORDER_NEAR, count);
+  int rc = run_passes(ctx, q, &launches);
   if (rc) return rc;
+  k_export<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, d_rays, ctx->hits.as<DevHit>(), d_hits, n);
+  launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(yart_hit), cudaMemcpyDeviceToHost, ctx->stream));
   unsigned long long c[2] = {0, 0};
@@ -657,7 +749,7 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
     stats->rays = n;
     stats->node_visits = c[0];
     stats->tri_tests = c[1];
-    stats->kernel_launches = 1;
+    stats->kernel_launches = launches;
     stats->gpu_ms = ms;
     stats->trace_ms = ms;
   }
@@ -723,8 +815,10 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
     CUDA_TRY(ctx, ctx->queue_b.reserve(cap * sizeof(uint32_t)));
     const uint32_t D = o->max_depth;
     const size_t n_counts = (size_t)D + 2;
+    const size_t n_obj_slots = (size_t)ctx->scene.n_objects + 1;
+    const size_t n_work = n_obj_slots * D;
     CUDA_TRY(ctx, ctx->counts.reserve(n_counts * sizeof(uint32_t)));
-    CUDA_TRY(ctx, ctx->work.reserve(n_counts * sizeof(uint32_t)));
+    CUDA_TRY(ctx, ctx->work.reserve(n_work * sizeof(uint32_t)));
     while (ctx->ev_pool.size() < 2 * (size_t)D) {
       cudaEvent_t e;
       CUDA_TRY(ctx, cudaEventCreate(&e));
@@ -753,39 +847,40 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
         R.sample_base = s0;
         R.spp_batch = spp;
         CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, n_counts * sizeof(uint32_t), ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(work, 0, n_counts * sizeof(uint32_t), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(work, 0, n_work * sizeof(uint32_t), ctx->stream));
         uint32_t* qa = ctx->queue_a.as<uint32_t>();
         uint32_t* qb = ctx->queue_b.as<uint32_t>();
         k_raygen<<<stream_grid, 256, 0, ctx->stream>>>(R, qa, counts + 1);
         launches++;
         uint32_t b_done = 0;
         for (uint32_t b = 1; b <= D; ++b) {
-          TraceParams P;
-          memset(&P, 0, sizeof(P));
-          P.scene = ctx->scene;
-          P.objects = ctx->scene.objects;
-          P.n_objects = ctx->scene.n_objects;
-          P.media_mask = ctx->has_media ? 1u : 0u;
-          P.rays = R.st.rays;
-          P.ray_time = R.st.time;
-          P.queue = qa;
-          P.n_items_dev = counts + b;
-          P.work_counter = work + b;
-          P.hits = R.st.hits;
-          P.counters = ctx->counters.as<unsigned long long>();
-          P.t_min = 0.001; // world.hit(ray_in, 0.001, f64::INFINITY) (main.rs:548)
-          P.t_max = INFINITY;
-          P.seed = o->seed;
-          P.bounce = b;
-          P.spp_batch = spp;
-          P.sample_base = s0;
-          P.pixel_base = p0;
+          QueryArgs q;
+          memset(&q, 0, sizeof(q));
+          q.c.rays = R.st.rays;
+          q.c.queue = qa;
+          q.c.n_items_dev = counts + b;
+          q.c.hits = R.st.hits;
+          q.c.t_min = 0.001; // world.hit(ray_in, 0.001, f64::INFINITY) (main.rs:548)
+          q.c.t_max = INFINITY;
+          q.d_objects = ctx->scene.objects;
+          q.h_objects = ctx->h_objects.data();
+          q.n_objects = ctx->scene.n_objects;
+          q.ray_time = R.st.time;
+          q.seed = o->seed;
+          q.bounce = b;
+          q.spp_batch = spp;
+          q.sample_base = s0;
+          q.pixel_base = p0;
+          q.work_counters = work + (size_t)(b - 1) * n_obj_slots;
+          q.counters = ctx->counters.as<unsigned long long>();
+          q.near = near;
+          q.count = count;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1)], ctx->stream));
-          rc = launch_trace(ctx, P, near, count);
+          rc = run_passes(ctx, q, &launches);
           if (rc) return rc;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1) + 1], ctx->stream));
           k_shade<<<stream_grid, 256, 0, ctx->stream>>>(R, qa, counts + b, qb, counts + b + 1, b);
-          launches += 2;
+          launches += 1;
           std::swap(qa, qb);
           b_done = b;
           // the tail of the bounce loop is nearly empty: look at the live count now and then
