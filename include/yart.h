@@ -230,7 +230,7 @@ typedef struct yart_stats {
   double gpu_ms;            /* CUDA-event time of the call's device work                        */
   double trace_ms;          /* ... of which closest-hit kernels                                 */
   uint32_t max_bounce;      /* deepest bounce that still had live paths                         */
-  uint32_t _pad;
+  uint32_t trace_launches;  /* ... of kernel_launches: closest-hit kernels (k_traverse / k_analytic) */
 } yart_stats;
 
 typedef struct yart_render_opts {

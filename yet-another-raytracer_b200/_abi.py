@@ -77,7 +77,7 @@ class Camera(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_double), ("trace_ms", C.c_double),
-                ("max_bounce", C.c_uint32), ("_pad", C.c_uint32)]
+                ("max_bounce", C.c_uint32), ("trace_launches", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}

@@ -750,6 +750,7 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
     stats->node_visits = c[0];
     stats->tri_tests = c[1];
     stats->kernel_launches = launches;
+    stats->trace_launches = (uint32_t)(launches - 1);
     stats->gpu_ms = ms;
     stats->trace_ms = ms;
   }
@@ -794,7 +795,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
     d_film = ctx->film.as<double>();
     CUDA_TRY(ctx, cudaMemcpyAsync(d_film, film_xyz, film_bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
-  uint64_t total_rays = 0, total_paths = 0, launches = 0;
+  uint64_t total_rays = 0, total_paths = 0, launches = 0, trace_launches = 0;
   double trace_ms = 0.0;
   uint32_t deepest = 0;
   if (n_samples > 0) {
@@ -876,7 +877,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
           q.near = near;
           q.count = count;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1)], ctx->stream));
-          rc = run_passes(ctx, q, &launches);
+          rc = run_passes(ctx, q, &trace_launches);
           if (rc) return rc;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1) + 1], ctx->stream));
           k_shade<<<stream_grid, 256, 0, ctx->stream>>>(R, qa, counts + b, qb, counts + b + 1, b);
@@ -920,7 +921,8 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
     stats->tri_tests = visit[1];
     stats->rays = total_rays;
     stats->paths = total_paths;
-    stats->kernel_launches = launches;
+    stats->kernel_launches = launches + trace_launches;
+    stats->trace_launches = (uint32_t)trace_launches;
     stats->gpu_ms = ms;
     stats->trace_ms = trace_ms;
     stats->max_bounce = deepest;
