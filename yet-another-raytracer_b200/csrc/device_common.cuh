@@ -115,6 +115,7 @@ struct DevMesh {
   const double* shade;  // 12 doubles per triangle (FlatTriShade: 9 normals + 6 float uvs)
   uint32_t root;
   uint32_t max_stack;
+  double bound[3];      // max |coordinate| per axis
 };
 
 // A flat 4-wide tree over the members of a BVHNode group (spheres / boxes).  Same 128-byte node

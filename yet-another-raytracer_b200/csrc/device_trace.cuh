@@ -255,8 +255,9 @@ struct TraverseParams {
   uint32_t node_threshold;    // leave the inner-node loop once fewer lanes than this are in it
   uint32_t _pad;
   double sin_theta, cos_theta, offset[3];
+  double bound[3];            // max |coordinate| of the mesh per axis (for the f32 slab error bound)
   uint32_t* work_counter;     // zero before launch
-  unsigned long long* counters; // [0] node visits, [1] triangle tests (COUNT only)
+  unsigned long long* counters; // [0] node visits, [1] triangle tests, [2] exact-fallback nodes (COUNT only)
 };
 
 struct AnalyticParams {
@@ -315,7 +316,12 @@ __device__ __noinline__ uint32_t box4_ieee(const float4* nd, double ox, double o
 #define YART_TRAVERSE_MIN_BLOCKS 4
 #endif
 
-template <bool NEAR, bool COUNT, int STACK>
+// MIXED selects how the four slab tests of a node are evaluated:
+//   false: f64 in the reference's operation order (after 24 f32->f64 conversions per node);
+//   true : a conservative f32 evaluation decides every box that is clearly hit or clearly missed
+//          and only the (rare) undecided ones are re-evaluated exactly in f64.  Both give the SAME
+//          hit mask as qbvh.rs:495-532 -- see the error bound at the f32 test below.
+template <bool NEAR, bool COUNT, int STACK, bool MIXED>
 __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_traverse(const TraverseParams P) {
   __shared__ uint32_t s_stack[STACK + 1][kTraceThreads];
   const int tid = threadIdx.x;
@@ -336,7 +342,10 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
   double t_best = 0, t_entry = 0, best_bu = 0, best_bv = 0;
   uint32_t best_prim = YART_MISS; // YART_MISS = this mesh has not produced a hit
   bool exhausted = false;         // the global queue is empty
-  unsigned long long n_nodes = 0, n_tris = 0;
+  unsigned long long n_nodes = 0, n_tris = 0, n_exact = 0;
+  // MIXED: the ray as f32 slab coefficients t = b*inv + c, and the absolute part of the error bound
+  float ixf = 0, iyf = 0, izf = 0, cxf = 0, cyf = 0, czf = 0, amax2 = 0, t_best_f = 0;
+  const float t_min_f = (float)t_min;
 
   for (;;) {
     // =============== phase A: retire finished rays, fetch new ones ================================
@@ -392,6 +401,21 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           sgn = NEAR ? (pos ^ 7u) : pos;
           // (b - o) * (1/d) can only be NaN when 1/d is infinite or the ray itself is not finite
           if (!(isfinite(ix) && isfinite(iy) && isfinite(iz) && isfinite(ox) && isfinite(oy) && isfinite(oz))) pos |= 8u;
+          if (MIXED) {
+            ixf = (float)ix; iyf = (float)iy; izf = (float)iz;
+            cxf = (float)(-(ox * ix)); cyf = (float)(-(oy * iy)); czf = (float)(-(oz * iz));
+            // |t32 - t64| <= 2^-24 (|b| + |o|) |inv| + 2^-24 |t32| (+ f64 roundings); doubled for margin:
+            // absolute part A = 2^-23 (B + |o|) |inv| maximised over the axes, kept as 2A (rounded up)
+            const double a = fmax(fmax((P.bound[0] + fabs(ox)) * fabs(ix), (P.bound[1] + fabs(oy)) * fabs(iy)),
+                                  (P.bound[2] + fabs(oz)) * fabs(iz));
+            amax2 = __double2float_ru(a * (1.0 / 4194304.0)); // 2A = 2^-22 * a
+            // rays whose f32 image is not well inside the normal range take the exact path throughout
+            const float lo = 1e-30f, hi = 1e30f;
+            const bool ok = fabsf(ixf) > lo && fabsf(ixf) < hi && fabsf(iyf) > lo && fabsf(iyf) < hi && fabsf(izf) > lo &&
+                            fabsf(izf) < hi && fabsf(cxf) < hi && fabsf(cyf) < hi && fabsf(czf) < hi && amax2 < hi;
+            if (!ok) pos |= 8u;
+            t_best_f = (float)t_best;
+          }
           cur = P.root;
           sp = 0;
           t_entry = t_best;
@@ -423,8 +447,41 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
         const uint32_t axes = __float_as_uint(cm8.hi.x);
         if (COUNT) n_nodes++;
         uint32_t hitmask = 0;
-        if (!(pos & 8u)) {
-          // Fast path.  All slab values are finite or +-inf, never NaN, and b_min <= b_max, so
+        if (MIXED && !(pos & 8u)) {
+          // Conservative f32 test.  Per slab t32 = fma(b, inv32, c32); near32 / far32 are the max / min over
+          // the entry / exit planes with t_min / t_best folded in.  With R = 2^-22 and A as above,
+          // |near32 - near64| <= R|near32| + A and the same for far, so
+          //   far32 - near32 >  R(|far32| + |near32|) + 2A  =>  far64 > near64   (the reference pushes)
+          //   far32 - near32 < -R(|far32| + |near32|) - 2A  =>  far64 < near64   (the reference does not)
+          // and everything in between (also any inf / NaN) is settled by the exact f64 test.
+          const bool px = (pos & 1u) != 0, py = (pos & 2u) != 0, pz = (pos & 4u) != 0;
+#define YART_SEL4(P_, A, B) make_float4((P_) ? A.x : B.x, (P_) ? A.y : B.y, (P_) ? A.z : B.z, (P_) ? A.w : B.w)
+          const float4 nx = YART_SEL4(px, sx8.lo, sx8.hi), fx = YART_SEL4(px, sx8.hi, sx8.lo);
+          const float4 ny = YART_SEL4(py, sy8.lo, sy8.hi), fy = YART_SEL4(py, sy8.hi, sy8.lo);
+          const float4 nz = YART_SEL4(pz, sz8.lo, sz8.hi), fz = YART_SEL4(pz, sz8.hi, sz8.lo);
+#undef YART_SEL4
+          uint32_t amb = 0;
+#define YART_BOX_F32(K, C)                                                                                  \
+  {                                                                                                         \
+    const float tn = fmaxf(fmaxf(t_min_f, fmaf(nx.C, ixf, cxf)), fmaxf(fmaf(ny.C, iyf, cyf), fmaf(nz.C, izf, czf))); \
+    const float tf = fminf(fminf(t_best_f, fmaf(fx.C, ixf, cxf)), fminf(fmaf(fy.C, iyf, cyf), fmaf(fz.C, izf, czf))); \
+    const float g = tf - tn;                                                                                \
+    const float e = fmaf(fabsf(tf) + fabsf(tn), 2.384185791015625e-7f, amax2);                              \
+    hitmask |= (g > e) ? (1u << (K)) : 0u;                                                                  \
+    amb |= ((g > e) || (g < -e)) ? 0u : (1u << (K));                                                        \
+  }
+          YART_BOX_F32(0, x)
+          YART_BOX_F32(1, y)
+          YART_BOX_F32(2, z)
+          YART_BOX_F32(3, w)
+#undef YART_BOX_F32
+          if (amb) {
+            if (COUNT) n_exact++;
+            const uint32_t exact = box4_ieee<NEAR>(nd, ox, oy, oz, 1.0 / dx, 1.0 / dy, 1.0 / dz, t_min, t_best);
+            hitmask = (hitmask & ~amb) | (exact & amb);
+          }
+        } else if (!MIXED && !(pos & 8u)) {
+          // Fast f64 path.  All slab values are finite or +-inf, never NaN, and b_min <= b_max, so
           // min(t0,t1) is the plane on the side the ray comes from and max(t0,t1) the other one:
           // identical values to qbvh.rs:495-519 with half the min/max work and no NaN handling.
           const bool px = (pos & 1u) != 0, py = (pos & 2u) != 0, pz = (pos & 4u) != 0;
@@ -450,7 +507,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           YART_BOX_FAST(3, w)
 #undef YART_BOX_FAST
         } else {
-          hitmask = box4_ieee<NEAR>(nd, ox, oy, oz, ix, iy, iz, t_min, t_best);
+          hitmask = box4_ieee<NEAR>(nd, ox, oy, oz, 1.0 / dx, 1.0 / dy, 1.0 / dz, t_min, t_best);
         }
         // ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]] (qbvh.rs:521-524)
         const uint32_t idx = (((sgn >> (axes & 3u)) & 1u) << 2) | (((sgn >> ((axes >> 2) & 3u)) & 1u) << 1) |
@@ -503,6 +560,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
         ok = ok && (NEAR ? ((t <= t_best) && (t < t_entry)) : (t_best > t));
         if (ok) {
           t_best = t; best_prim = first + i; best_bu = u; best_bv = v;
+          if (MIXED) t_best_f = (float)t;
         }
       }
       if (sp == 0) {
@@ -516,6 +574,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
   if (COUNT) {
     atomicAdd(&P.counters[0], n_nodes);
     atomicAdd(&P.counters[1], n_tris);
+    atomicAdd(&P.counters[2], n_exact);
   }
 }
 

@@ -299,13 +299,17 @@ int grid_for(yart_ctx* ctx, const void* kernel, int threads, int* grid) {
 }
 
 typedef void (*TraverseKernel)(const TraverseParams);
-TraverseKernel pick_traverse_kernel(bool near, bool count, uint32_t max_stack) {
+template <bool MIXED>
+TraverseKernel pick_traverse_kernel_m(bool near, bool count, uint32_t max_stack) {
   if (max_stack <= 32) {
-    if (near) return count ? k_traverse<true, true, 32> : k_traverse<true, false, 32>;
-    return count ? k_traverse<false, true, 32> : k_traverse<false, false, 32>;
+    if (near) return count ? k_traverse<true, true, 32, MIXED> : k_traverse<true, false, 32, MIXED>;
+    return count ? k_traverse<false, true, 32, MIXED> : k_traverse<false, false, 32, MIXED>;
   }
-  if (near) return count ? k_traverse<true, true, 64> : k_traverse<true, false, 64>;
-  return count ? k_traverse<false, true, 64> : k_traverse<false, false, 64>;
+  if (near) return count ? k_traverse<true, true, 64, MIXED> : k_traverse<true, false, 64, MIXED>;
+  return count ? k_traverse<false, true, 64, MIXED> : k_traverse<false, false, 64, MIXED>;
+}
+TraverseKernel pick_traverse_kernel(bool near, bool count, uint32_t max_stack, bool mixed) {
+  return mixed ? pick_traverse_kernel_m<true>(near, count, max_stack) : pick_traverse_kernel_m<false>(near, count, max_stack);
 }
 
 int tune_env(const char* name, int dflt) {
@@ -332,6 +336,7 @@ struct QueryArgs {
 int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
   static const int rt = tune_env("YART_TUNE_RT", 8), nt = tune_env("YART_TUNE_NT", 12);
   static const int carve = tune_env("YART_TUNE_CARVEOUT", 35);
+  static const int mixed = tune_env("YART_TUNE_MIXED", 1); // 0: all-f64 slab tests (same results, slower)
   bool first = true;
   uint32_t i = 0, n_trav = 0;
   auto is_mesh = [&](uint32_t k) {
@@ -368,7 +373,8 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       for (int k = 0; k < 3; ++k) T.offset[k] = o.offset[k];
       T.work_counter = q.work_counters + n_trav++;
       T.counters = q.counters;
-      TraverseKernel k = pick_traverse_kernel(q.near, q.count, ctx->max_stack);
+      for (int k = 0; k < 3; ++k) T.bound[k] = m.bound[k];
+      TraverseKernel k = pick_traverse_kernel(q.near, q.count, ctx->max_stack, mixed != 0);
       int per_sm = 0;
       CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(k), kTraceThreads, 0));
       // leave everything the stacks do not need to L1: the tree's upper levels live there
@@ -561,6 +567,7 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
     meshes[i].shade = reinterpret_cast<const double*>(ds);
     meshes[i].root = q.root;
     meshes[i].max_stack = q.max_stack;
+    for (int a = 0; a < 3; ++a) meshes[i].bound[a] = std::fmax(std::fabs(q.bbox_min[a]), std::fabs(q.bbox_max[a]));
     ctx->max_stack = std::max(ctx->max_stack, q.max_stack);
     memset(&solo[i], 0, sizeof(yart_object));
     solo[i].kind = YART_OBJ_MESH;
