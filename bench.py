@@ -7,8 +7,8 @@
 Workload (BASELINE.json configs[2], the one its `metric` is quoted on): the `david` preset
 (david.obj, 46,664 triangles, white Lambertian mesh + a rotated glass instance + 5 sphere lights)
 at 1920x1080, max-depth 50, 1024 spp.  A STEP is one wavefront pass of the hot path over one batch:
-`spp_per_step` (8) samples of every pixel of the frame = 16.6 M camera paths, ~71 M world rays,
-with the scene resident in HBM.  The default K = 128 steps is the whole 1024-spp job.
+`spp_per_step` (32) samples of every pixel of the frame = 66 M camera paths, ~237 M world rays,
+with the scene resident in HBM.  The default K = 32 steps is the whole 1024-spp job.
 With N GPUs every rank renders its own sample range each step (scene replicated, weak scaling:
 per-GPU work is fixed) and the f64 XYZ films are combined with one NCCL reduce inside the timed
 region.  All timing is on the device (CUDA events on the launching stream), max over ranks.
@@ -35,7 +35,7 @@ if str(ROOT) not in sys.path:
 
 SCENE = "david"
 WIDTH, HEIGHT, MAX_DEPTH, TOTAL_SPP = 1920, 1080, 50, 1024
-SPP_PER_STEP = 8
+SPP_PER_STEP = 32
 SEED = 1
 METRIC = "Mrays/s (primary+secondary) on david.obj 1920x1080 max-depth 50"
 # bytes one ray moves besides node/triangle fetches: 48 B ray + 8 B time + 4 B queue entry read,
@@ -239,7 +239,7 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
 
     # ---- timed region 2: end to end through the C ABI with HOST buffers (`e2e`) ----
-    K2 = min(K, 16)
+    K2 = min(K, 8)
     host_film = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.float64).pin_memory()
     hf = host_film.numpy()
     ctx.render(cam, WIDTH, HEIGHT, 0, SPP_PER_STEP, MAX_DEPTH, SEED, order, SPP_PER_STEP, film=hf)  # warm the path
@@ -298,11 +298,11 @@ def run_ours(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "david 1920x1080 max-depth 50, %d spp per step per GPU (BASELINE configs[2]; K=128 "
-                            "steps = the 1024-spp job)" % SPP_PER_STEP,
+                "workload": "david 1920x1080 max-depth 50, %d spp per step per GPU (BASELINE configs[2]; K=%d "
+                            "steps = the 1024-spp job)" % (SPP_PER_STEP, TOTAL_SPP // SPP_PER_STEP),
                 "scene": SCENE, "width": WIDTH, "height": HEIGHT, "max_depth": MAX_DEPTH, "spp_per_step": SPP_PER_STEP,
                 "spp_total": SPP_PER_STEP * K * N, "seed": SEED, "traversal_order": "near (bit-identical hits)",
-                "l2": "inputs larger than L2: 2.3 GB of path state streams per step; the 5.9 MB QBVH is meant to "
+                "l2": "inputs larger than L2: 9 GB of path state streams per step; the 7 MB scene is meant to "
                       "stay L2-resident",
                 "parallelism": "sample-range sharding x%d, scene replicated, one NCCL reduce of the f64 film" % N,
             },

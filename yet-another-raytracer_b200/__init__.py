@@ -23,7 +23,7 @@ from ._abi import (FLAG_COUNT_VISITS, FLAG_DEVICE_PTRS, HIT_DTYPE, MISS, ORDER_N
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "libyart_b200.so"
+LIB_PATH = Path(os.environ.get("YART_LIB_PATH", PKG_DIR / "libyart_b200.so"))  # (override: A/B builds)
 
 SCENE_NAMES = ["random-scene", "two-spheres", "two-perlin-spheres", "earth", "simple-light", "cornell-box",
                "cornell-box-smoke", "next-week-final", "teapot", "bunny", "three-spheres", "sycee", "david"]

@@ -32,8 +32,9 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "--shared", "-cudart", "shared",
 ]
-if os.environ.get("YART_TRAVERSE_MIN_BLOCKS"):  # tuning knob: resident blocks per SM the kernel is compiled for
-    NVCC_FLAGS += ["-DYART_TRAVERSE_MIN_BLOCKS=" + os.environ["YART_TRAVERSE_MIN_BLOCKS"]]
+for knob in ("YART_TRAVERSE_MIN_BLOCKS", "YART_SHADE_MIN_BLOCKS"):  # tuning: resident blocks per SM compiled for
+    if os.environ.get(knob):
+        NVCC_FLAGS += ["-D%s=%s" % (knob, os.environ[knob])]
 
 
 def _digest():

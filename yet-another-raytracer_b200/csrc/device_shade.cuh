@@ -535,7 +535,10 @@ __global__ void __launch_bounds__(256) k_camera_rays(const RenderParams R, yart_
 // One bounce of ray_reflectance (main.rs:537-588) for every queued path.  Surviving paths are
 // appended to the next queue (warp-aggregated atomics = stream compaction); finished paths write
 // their sample value.  `bounce` is 1-based: the bounce-th world.hit of the path.
-__global__ void __launch_bounds__(256) k_shade(const RenderParams R, const uint32_t* queue, const uint32_t* queue_count,
+#ifndef YART_SHADE_MIN_BLOCKS
+#define YART_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const RenderParams R, const uint32_t* queue, const uint32_t* queue_count,
                                                 uint32_t* next_queue, uint32_t* next_count, uint32_t bounce) {
   const DevScene& S = R.scene;
   const uint32_t n = *queue_count;

@@ -807,11 +807,13 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
   uint32_t deepest = 0;
   if (n_samples > 0) {
     // batch shape: whole frame x spp_batch, or pixel chunks when the frame alone is too large
-    const uint64_t kMaxPaths = 1ull << 24; // 16 Mi paths in flight (~2.3 GB of path state)
+    // Big batches: every batch pays ~12 ms of fixed cost (4 launches per bounce x 50 bounces, nearly empty
+    // tail bounces), so put up to 64 Mi paths in flight (136 B of state each = 9 GB of the 180 GB).
+    const uint64_t kMaxPaths = 1ull << 26;
     uint32_t spp_batch = o->batch_spp ? o->batch_spp : (uint32_t)std::max<uint64_t>(1, kMaxPaths / n_pixels_total);
     spp_batch = std::min(spp_batch, n_samples);
     uint32_t pix_chunk = n_pixels_total;
-    if ((uint64_t)pix_chunk * spp_batch > 4 * kMaxPaths) pix_chunk = (uint32_t)(4 * kMaxPaths / spp_batch);
+    if ((uint64_t)pix_chunk * spp_batch > kMaxPaths) pix_chunk = (uint32_t)std::max<uint64_t>(1, kMaxPaths / spp_batch);
     const uint64_t cap = (uint64_t)pix_chunk * spp_batch;
     CUDA_TRY(ctx, ctx->rays.reserve(cap * sizeof(yart_ray)));
     CUDA_TRY(ctx, ctx->time.reserve(cap * sizeof(double)));
