@@ -542,13 +542,48 @@ __global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const Rend
                                                 uint32_t* next_queue, uint32_t* next_count, uint32_t bounce) {
   const DevScene& S = R.scene;
   const uint32_t n = *queue_count;
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Paths of one block are regrouped by what their hit needs (miss / emitter, Lambertian, dielectric,
+  // other) before shading, so the warps run mostly one branch of the material switch.  Which thread
+  // shades which path does not matter: every result is addressed by the path id.
+  __shared__ uint32_t s_ids[256];
+  __shared__ uint32_t s_cnt[8][4];
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    {
+      const uint32_t it = base + threadIdx.x;
+      uint32_t my_id = YART_MISS, cls = 4;
+      if (it < n) {
+        my_id = queue[it];
+        const uint32_t obj = R.st.hits[my_id].obj;
+        cls = 0;
+        if (obj != YART_MISS) {
+          const uint32_t kind = S.materials[S.objects[obj].material].kind;
+          cls = (kind == YART_MAT_LAMBERTIAN) ? 1u : ((kind == YART_MAT_DIELECTRIC) ? 2u
+                : ((kind == YART_MAT_NONE || kind == YART_MAT_DIFFUSE_LIGHT) ? 0u : 3u));
+        }
+      }
+      uint32_t rank = 0;
+#pragma unroll
+      for (uint32_t c = 0; c < 4; ++c) {
+        const uint32_t b = __ballot_sync(0xffffffffu, cls == c);
+        if (cls == c) rank = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[warp][c] = __popc(b);
+      }
+      __syncthreads();
+      if (cls < 4) {
+        uint32_t off = 0;
+        for (uint32_t c = 0; c < cls; ++c)
+          for (uint32_t w = 0; w < 8; ++w) off += s_cnt[w][c];
+        for (uint32_t w = 0; w < warp; ++w) off += s_cnt[w][cls];
+        s_ids[off + rank] = my_id;
+      }
+      __syncthreads();
+    }
     const uint32_t item = base + threadIdx.x;
     bool alive = false;
     uint32_t id = 0;
     if (item < n) {
-      id = queue[item];
+      id = s_ids[threadIdx.x];
       const uint32_t pixel = R.pixel_base + id / R.spp_batch;
       const uint32_t sample = R.sample_base + id % R.spp_batch;
       const Rng rng = make_rng(R.seed, pixel, sample);
@@ -670,6 +705,7 @@ __global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const Rend
       pos = __shfl_sync(0xffffffffu, pos, leader);
       if (alive) next_queue[pos + __popc(ballot & ((1u << lane) - 1u))] = id;
     }
+    __syncthreads(); // s_ids / s_cnt are rewritten by the next round
   }
 }
 

@@ -907,12 +907,18 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
         CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), counts, n_counts * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         total_paths += h_counts[1];
+        static const int debug_bounces = tune_env("YART_DEBUG_BOUNCES", 0);
         for (uint32_t b = 1; b <= b_done; ++b) {
           total_rays += h_counts[b];
           if (h_counts[b]) deepest = std::max(deepest, b);
           float ms = 0.f;
           CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_pool[2 * (b - 1)], ctx->ev_pool[2 * (b - 1) + 1]));
           trace_ms += ms;
+          if (debug_bounces) {
+            float gap = 0.f; // from the end of this bounce's closest-hit stage to the start of the next one
+            if (b < b_done) cudaEventElapsedTime(&gap, ctx->ev_pool[2 * (b - 1) + 1], ctx->ev_pool[2 * b]);
+            fprintf(stderr, "bounce %2u: rays %9u  closest-hit %8.3f ms  shade+gap %8.3f ms\n", b, h_counts[b], ms, gap);
+          }
         }
       }
     }
