@@ -69,6 +69,7 @@ def lib():
         "orc_camera_rays": (i32, [P(abi.Camera), P(abi.RenderOpts), vp, vp, vp]),
         "orc_dump_path_rays": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, u64, P(u64)]),
         "orc_sample": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), u32, u32, vp, P(u32)]),
+        "orc_sample_path": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), u32, u32, vp, u64, P(u64)]),
         "orc_sanitize_sample_xyz": (None, [vp, vp]),
         "orc_clamp_display_channel": (C.c_uint8, [f64]),
         "orc_gamma_corrected": (None, [vp, vp]),
@@ -167,6 +168,14 @@ class Scene:
         n = C.c_uint64()
         o = _opts(width, height, sample_begin, sample_end, max_depth, seed, abi.ORDER_REFERENCE)
         _check(lib().orc_dump_path_rays(self._h, C.byref(camera), C.byref(o), rays.ctypes.data, cap, C.byref(n)))
+        return rays[:n.value].copy()
+
+    def sample_path(self, camera, width, height, pixel, sample, max_depth=50, seed=1):
+        rays = np.empty(max_depth + 1, dtype=abi.RAY_DTYPE)
+        n = C.c_uint64()
+        o = _opts(width, height, sample, sample + 1, max_depth, seed, abi.ORDER_REFERENCE)
+        _check(lib().orc_sample_path(self._h, C.byref(camera), C.byref(o), pixel, sample, rays.ctypes.data, len(rays),
+                                     C.byref(n)))
         return rays[:n.value].copy()
 
     def sample(self, camera, width, height, pixel, sample, max_depth=50, seed=1):

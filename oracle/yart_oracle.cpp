@@ -1504,6 +1504,21 @@ int orc_dump_path_rays(const orc_scene* s, const yart_camera* cam, const yart_re
   return YART_OK;
 }
 
+int orc_sample_path(const orc_scene* s, const yart_camera* cam, const yart_render_opts* o, uint32_t pixel,
+                    uint32_t sample, yart_ray* rays, uint64_t cap, uint64_t* n_out) {
+  if (!s || !cam || !o || !rays || !n_out) { g_err = "null argument"; return YART_ERR_INVALID; }
+  const Camera k = make_camera(*cam);
+  std::vector<Factor> scratch;
+  std::vector<yart_ray> dump;
+  HitCtx c{&s->s, o->order, nullptr};
+  double xyz[3];
+  render_sample(c, k, *o, pixel % o->width, pixel / o->width, sample, xyz, nullptr, scratch, &dump);
+  uint64_t n = std::min<uint64_t>(cap, dump.size());
+  for (uint64_t i = 0; i < n; ++i) rays[i] = dump[i];
+  *n_out = n;
+  return YART_OK;
+}
+
 int orc_sample(const orc_scene* s, const yart_camera* cam, const yart_render_opts* o, uint32_t pixel,
                uint32_t sample, double* xyz3, uint32_t* n_rays) {
   if (!s || !cam || !o || !xyz3) { g_err = "null argument"; return YART_ERR_INVALID; }

@@ -76,6 +76,9 @@ int orc_camera_rays(const yart_camera* cam, const yart_render_opts* opts, yart_r
 /* all world rays (every bounce) of the samples in opts, up to cap; for the path-ray sweep */
 int orc_dump_path_rays(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
                        yart_ray* rays, uint64_t cap, uint64_t* n_out);
+/* the world rays (one per bounce) of one sample (debugging parity) */
+int orc_sample_path(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
+                    uint32_t pixel, uint32_t sample, yart_ray* rays, uint64_t cap, uint64_t* n_out);
 /* one sample's value before sanitising + its ray count (debugging parity) */
 int orc_sample(const orc_scene* s, const yart_camera* cam, const yart_render_opts* opts,
                uint32_t pixel, uint32_t sample, double* xyz3, uint32_t* n_rays);

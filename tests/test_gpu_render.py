@@ -138,3 +138,18 @@ def test_non_multiple_of_8_frames_follow_the_reference_tiling(yart, orc, ctx):
 
     mask = covered(h)[:, None] & covered(w)[None, :]
     assert mask.sum() == st.paths // 4 and (got[~mask] == 0).all() and (got[mask].sum(axis=-1) != 0).mean() > 0.5
+
+
+def test_cli_writes_a_png(yart, tmp_path):
+    import importlib
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    cli = importlib.import_module("yart_cli")
+    out = tmp_path / "sub" / "cornell.png"
+    assert cli.main(["--scene", "cornell-box", "--width", "64", "--samples", "4", "--output", str(out)]) == 0
+    from PIL import Image
+    im = Image.open(out)
+    assert im.size == (64, 64) and im.mode == "RGBA"
+    px = np.asarray(im)
+    assert (px[..., 3] == 255).all() and px[..., :3].mean() > 5

@@ -196,3 +196,19 @@ def test_perlin_tables_are_permutations(yart):
             assert sorted(perm) == list(range(256))
         v = np.array([list(p.perlins[k].ranvec[i]) for i in range(256)])
         assert (np.abs(v) < 1).all() and (np.array(list(p.perlins[k].ranfloat)) < 1).all()
+
+
+def test_cli_parses_like_the_reference():  # main.rs:831-842 and parse_positive_usize :148-158
+    import importlib
+    import sys
+    sys.path.insert(0, str(ROOT))
+    cli = importlib.import_module("yart_cli")
+    y = importlib.import_module("yet-another-raytracer_b200")
+    p = cli.build_parser(y.SCENE_NAMES)
+    a = p.parse_args(["--scene", "david"])
+    assert a.scene == "david" and a.width is None and a.samples is None
+    a = p.parse_args(["--scene", "cornell-box", "--width", "400", "--samples", "32", "--max-depth", "50"])
+    assert (a.width, a.samples, a.max_depth) == (400, 32, 50)
+    for bad in (["--scene", "not-a-scene"], ["--scene", "david", "--samples", "0"], ["--scene", "david", "--width", "-3"], []):
+        with pytest.raises(SystemExit):
+            p.parse_args(bad)
