@@ -327,6 +327,17 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31;
   const uint64_t n_items = P.c.n_items_dev ? (uint64_t)*P.c.n_items_dev : P.c.n_items;
+  // Work distribution: warp w starts with items [32w, 32w+32) without touching the counter and only then
+  // fetches dynamically from total_warps*32 + atomicAdd(counter).  Warps whose first slice is already past
+  // the end leave at once -- a nearly empty queue (the deep bounces) costs no same-address atomics.
+  // A short queue is spread thinly (rpw < 32 rays per warp): a warp's run time is the serialised work of
+  // its most divergent rays, so a deep bounce with a few hundred rays finishes sooner on many warps.
+  const uint32_t warp_global = (blockIdx.x * kTraceThreads + tid) >> 5;
+  const uint64_t total_warps = (uint64_t)gridDim.x * (kTraceThreads / 32);
+  const uint32_t rpw = (uint32_t)max((unsigned long long)1, min((unsigned long long)32, (unsigned long long)((n_items + total_warps - 1) / total_warps)));
+  const uint64_t dyn_base = total_warps * rpw;
+  if ((uint64_t)warp_global * rpw >= n_items) return;
+  bool first_fetch = true;
   const uint32_t RT = P.refill_threshold, NT = P.node_threshold;
   const float4* __restrict__ nodes = P.nodes;
   const float4* __restrict__ tris = P.tris;
@@ -368,12 +379,20 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
       }
       const uint32_t fmask = __ballot_sync(a_mask, !exhausted);
       if (!exhausted) { // fetch: one atomic for all fetching lanes of the warp
-        const int leader = __ffs(fmask) - 1;
-        const uint32_t rank = __popc(fmask & ((1u << lane) - 1u));
-        uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(fmask));
-        base = __shfl_sync(fmask, base, leader);
-        const uint64_t item = (uint64_t)base + rank;
+        uint64_t item;
+        if (first_fetch) { // (all 32 lanes of the warp are here together the first time)
+          item = (lane < rpw) ? (uint64_t)warp_global * rpw + lane : n_items;
+          first_fetch = false;
+        } else if (dyn_base >= n_items) {
+          item = n_items; // nothing beyond the static slices: no need to touch the counter
+        } else {
+          const int leader = __ffs(fmask) - 1;
+          const uint32_t rank = __popc(fmask & ((1u << lane) - 1u));
+          uint32_t base = 0;
+          if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(fmask));
+          base = __shfl_sync(fmask, base, leader);
+          item = dyn_base + base + rank;
+        }
         if (item >= n_items) {
           exhausted = true;
         } else {
@@ -509,18 +528,22 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
         } else {
           hitmask = box4_ieee<NEAR>(nd, ox, oy, oz, 1.0 / dx, 1.0 / dy, 1.0 / dz, t_min, t_best);
         }
-        // ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]] (qbvh.rs:521-524)
-        const uint32_t idx = (((sgn >> (axes & 3u)) & 1u) << 2) | (((sgn >> ((axes >> 2) & 3u)) & 1u) << 1) |
-                             ((sgn >> ((axes >> 4) & 3u)) & 1u);
-        const uint32_t enc = (uint32_t)(((idx & 4u) ? kOrderHi : kOrderLo) >> (16u * (idx & 3u))) & 0xFFFFu;
-        // push_hit_children (qbvh.rs:18-31), branch-free: always store to the next free slot, advance
-        // the cursor only for hit lanes
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t i = (enc >> (4 * j)) & 3u;
-          const uint32_t c01 = (i & 1u) ? ch.y : ch.x, c23 = (i & 1u) ? ch.w : ch.z;
-          s_stack[sp][tid] = (i & 2u) ? c23 : c01;
-          sp += (int)((hitmask >> i) & 1u);
+        // push_hit_children (qbvh.rs:18-31) in the order ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]]
+        // (qbvh.rs:14-16, 521-524) gives.  The table has structure: bit `top` says whether the left pair
+        // {0,1} is pushed before the right pair {2,3}; `left` whether 0 goes before 1, `right` whether 2 goes
+        // before 3.  So every hit child's stack slot is a closed form of the hit bits -- four predicated
+        // stores, no table, no serial loop.
+        {
+          const uint32_t T = (sgn >> (axes & 3u)) & 1u, L = (sgn >> ((axes >> 2) & 3u)) & 1u,
+                         Rr = (sgn >> ((axes >> 4) & 3u)) & 1u;
+          const uint32_t h0 = hitmask & 1u, h1 = (hitmask >> 1) & 1u, h2 = (hitmask >> 2) & 1u, h3 = (hitmask >> 3) & 1u;
+          const uint32_t nl = h0 + h1, nr = h2 + h3;
+          const uint32_t bl = T ? 0u : nr, br = T ? nl : 0u; // slots taken by the pair pushed first
+          if (h0) s_stack[sp + bl + (L ? 0u : h1)][tid] = ch.x;
+          if (h1) s_stack[sp + bl + (L ? h0 : 0u)][tid] = ch.y;
+          if (h2) s_stack[sp + br + (Rr ? 0u : h3)][tid] = ch.z;
+          if (h3) s_stack[sp + br + (Rr ? h2 : 0u)][tid] = ch.w;
+          sp += (int)(nl + nr);
         }
         if (sp == 0) {
           cur = kSentinel;

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -65,6 +66,11 @@ namespace {
       return YART_ERR_CUDA;                                                                  \
     }                                                                                        \
   } while (0)
+
+int tune_env(const char* name, int dflt) { // tuning / debugging knobs from the environment
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 
 struct DevBuf {
   void* p = nullptr;
@@ -215,6 +221,7 @@ struct yart_ctx {
   std::vector<void*> scene_allocs;
   DevScene scene;
   yart_object* d_solo = nullptr; // one un-wrapped MESH object per mesh, for mesh-only queries
+  std::map<const void*, int> traverse_blocks; // resident CTAs per SM of each k_traverse variant
   std::vector<yart_object> h_objects; // host copy of the world list: the pass plan is made on the host
   std::vector<DevMesh> h_meshes;
   uint32_t n_meshes = 0;
@@ -312,11 +319,6 @@ TraverseKernel pick_traverse_kernel(bool near, bool count, uint32_t max_stack, b
   return mixed ? pick_traverse_kernel_m<true>(near, count, max_stack) : pick_traverse_kernel_m<false>(near, count, max_stack);
 }
 
-int tune_env(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 // What is the same for every pass of one closest-hit query.
 struct QueryArgs {
   PassCommon c;
@@ -375,11 +377,16 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       T.counters = q.counters;
       for (int k = 0; k < 3; ++k) T.bound[k] = m.bound[k];
       TraverseKernel k = pick_traverse_kernel(q.near, q.count, ctx->max_stack, mixed != 0);
-      int per_sm = 0;
-      CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(k), kTraceThreads, 0));
-      // leave everything the stacks do not need to L1: the tree's upper levels live there
-      cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-      k<<<std::max(per_sm, 1) * ctx->sm_count, kTraceThreads, 0, ctx->stream>>>(T); // persistent: one resident wave
+      // occupancy query + carveout once per kernel variant (they cost tens of microseconds of host time,
+      // which is the whole budget of a deep bounce)
+      int& per_sm = ctx->traverse_blocks[(const void*)k];
+      if (per_sm == 0) {
+        // leave everything the stacks do not need to L1: the tree's upper levels live there
+        cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(k), kTraceThreads, 0));
+        per_sm = std::max(per_sm, 1);
+      }
+      k<<<per_sm * ctx->sm_count, kTraceThreads, 0, ctx->stream>>>(T); // persistent: one resident wave
       i++;
     } else {
       uint32_t j = i;
