@@ -101,6 +101,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def profiled_traffic_per_ray():
+    """DRAM bytes per ray per k_traverse launch from the committed ncu capture (profiles/r1_traffic.json)."""
+    try:
+        return float(json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())["dram_bytes_per_ray_per_launch"])
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -315,7 +323,11 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": "closest-hit stage (k_traverse x2 instances + k_analytic per bounce; k_traverse is ~93 % of it)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": (profiled_traffic_per_ray() * rays / trace_launches) if profiled_traffic_per_ray() else None,
+                "traffic_note": "bytes per k_traverse launch = 91.9 B/ray (dram read+write from the ncu --set full capture in "
+                                "profiles/r1_traffic.json) x this run's rays per launch; ~20x below the algorithmic bytes because "
+                                "node/triangle fetches hit L1/L2",
                 "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "trace_launches": int(trace_launches),
                 "avg_launch_ms": trace_ms / trace_launches, "trace_share_of_step": trace_ms / ms if ms else None,
