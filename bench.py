@@ -324,9 +324,9 @@ def run_ours(args):
             "roofline": {
                 "bound": "hbm", "kernel": "closest-hit stage (k_traverse x2 instances + k_analytic per bounce; k_traverse is ~93 % of it)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": (profiled_traffic_per_ray() * rays / trace_launches) if profiled_traffic_per_ray() else None,
+                "traffic": (profiled_traffic_per_ray() * rays / (trace_launches / 3.0)) if profiled_traffic_per_ray() else None,
                 "traffic_note": "bytes per k_traverse launch = 91.9 B/ray (dram read+write from the ncu --set full capture in "
-                                "profiles/r1_traffic.json) x this run's rays per launch; ~20x below the algorithmic bytes because "
+                                "profiles/r1_traffic.json) x this run's average rays per k_traverse launch (3 closest-hit launches per bounce); ~20x below the algorithmic bytes because "
                                 "node/triangle fetches hit L1/L2",
                 "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "trace_launches": int(trace_launches),
