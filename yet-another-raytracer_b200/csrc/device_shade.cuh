@@ -105,6 +105,9 @@ YART_DEV void prim_record(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
                           double bu, double bv, HitRec& rec) {
   rec.t = t;
   rec.material = o.material;
+  // get_sphere_uv (acos + atan2) only feeds ImageTexture::value; skip it when this material cannot read u, v
+  const yart_material& pm = S.materials[o.material];
+  const bool need_uv = pm.kind != YART_MAT_NONE && pm.kind != YART_MAT_DIELECTRIC && S.textures[pm.texture].kind == YART_TEX_IMAGE;
   switch (o.kind) {
     case YART_OBJ_SPHERE: { // sphere.rs:68-85
       const D3 center = d3(o.p[0], o.p[1], o.p[2]);
@@ -116,7 +119,8 @@ YART_DEV void prim_record(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
       } else {
         rec.normal = outward; rec.front_face = dot(rd, outward) < 0.0;
       }
-      get_sphere_uv(outward, rec.u, rec.v);
+      rec.u = rec.v = 0.0;
+      if (need_uv) get_sphere_uv(outward, rec.u, rec.v);
       break;
     }
     case YART_OBJ_MOVING_SPHERE: { // sphere.rs:175-197
@@ -128,7 +132,8 @@ YART_DEV void prim_record(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
       } else {
         rec.normal = -outward; rec.front_face = false;
       }
-      get_sphere_uv(outward, rec.u, rec.v);
+      rec.u = rec.v = 0.0;
+      if (need_uv) get_sphere_uv(outward, rec.u, rec.v);
       break;
     }
     case YART_OBJ_XY_RECT:
