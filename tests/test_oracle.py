@@ -253,3 +253,28 @@ def test_spectral_pipeline_facts(orc):
         orc.lib().orc_xyz_from_wavelength(float(wl), xyz.ctypes.data)
         tot += xyz[1]
     assert abs(tot - 106.856895) < 1e-3
+
+
+def test_closed_form_push_slots_equal_order_table():
+    """k_traverse does not walk ORDER_TABLE (qbvh.rs:14-31); it computes every hit child's stack slot in closed
+    form from the three sign bits (device_trace.cuh).  Check the formula against the table for all 8 x 16 cases."""
+    ORDER_TABLE = [0x0123, 0x0132, 0x1023, 0x1032, 0x2301, 0x3201, 0x2310, 0x3210]
+    for idx in range(8):
+        T, L, R = (idx >> 2) & 1, (idx >> 1) & 1, idx & 1
+        order = [(ORDER_TABLE[idx] >> (4 * j)) & 0xF for j in range(4)]
+        for hitmask in range(16):
+            h = [(hitmask >> k) & 1 for k in range(4)]
+            want = {}  # child -> slot, by push_hit_children
+            cursor = 0
+            for i in order:
+                if h[i]:
+                    want[i] = cursor
+                    cursor += 1
+            nl, nr = h[0] + h[1], h[2] + h[3]
+            bl, br = (0 if T else nr), (nl if T else 0)
+            got = {}
+            if h[0]: got[0] = bl + (0 if L else h[1])
+            if h[1]: got[1] = bl + (h[0] if L else 0)
+            if h[2]: got[2] = br + (0 if R else h[3])
+            if h[3]: got[3] = br + (h[2] if R else 0)
+            assert got == want, (idx, hitmask)

@@ -18,9 +18,6 @@ namespace yart {
 constexpr int kTraceThreads = 128;
 constexpr uint32_t kSentinel = 0x7FFFFFFFu; // "no traversal in progress" (never a valid node id)
 
-// ORDER_TABLE (qbvh.rs:14-16) packed 16 bits per entry
-constexpr unsigned long long kOrderLo = 0x1032102301320123ULL; // entries 0..3
-constexpr unsigned long long kOrderHi = 0x3210231032012301ULL; // entries 4..7
 
 // ---------------------------------------------------------------------------------------------
 // analytic primitives, t-only (the shade stage rebuilds the full HitRecord from t)

@@ -297,14 +297,6 @@ DevCamera make_camera(const yart_camera& c) { // Camera::new (camera.rs:41-80), 
   return k;
 }
 
-int grid_for(yart_ctx* ctx, const void* kernel, int threads, int* grid) {
-  int per_sm = 0;
-  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
-  if (per_sm < 1) per_sm = 1;
-  *grid = per_sm * ctx->sm_count; // persistent: exactly one resident wave on the 148 SMs
-  return YART_OK;
-}
-
 typedef void (*TraverseKernel)(const TraverseParams);
 template <bool MIXED>
 TraverseKernel pick_traverse_kernel_m(bool near, bool count, uint32_t max_stack) {
