@@ -1,6 +1,7 @@
 """Builds libyart_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
     python yet-another-raytracer_b200/build.py [--force] [--verbose]
+    python yet-another-raytracer_b200/build.py --bounds-check    (-> libyart_b200_checked.so, see below)
 
 Flags that matter:
   -gencode arch=compute_100a,code=sm_100a   B200 only, no PTX for other archs
@@ -8,6 +9,11 @@ Flags that matter:
                                             bit-exact closest-hit parity needs the same roundings
   -Xcompiler -ffp-contract=off              same for the host-side QBVH build / camera maths
   -lineinfo                                 so ncu's source page maps SASS back to these files
+
+--bounds-check builds a second library with -DYART_BOUNDS_CHECK: every index the kernels form (tree nodes,
+triangle records, traversal stack, ray / hit / queue slots) is checked and a violation traps.  It stands in
+for compute-sanitizer, which the GPU pool does not offer; run it with
+YART_LIB_PATH=yet-another-raytracer_b200/libyart_b200_checked.so (tests/test_gpu_bounds.py does).
 """
 import hashlib
 import os
@@ -19,6 +25,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 ROOT = PKG.parent
 LIB = PKG / "libyart_b200.so"
+LIB_CHECKED = PKG / "libyart_b200_checked.so"
 STAMP = PKG / ".build_stamp"
 
 SOURCES = ["host_obj.cpp", "host_qbvh.cpp", "host_presets.cpp", "host_api.cpp", "yart_device.cu"]
@@ -52,22 +59,25 @@ def nvcc_path():
     return "nvcc"
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, bounds_check=False):
     digest = _digest()
-    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
-        return str(LIB)
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    lib = LIB_CHECKED if bounds_check else LIB
+    stamp = PKG / (".build_stamp_checked" if bounds_check else ".build_stamp")
+    if not force and lib.exists() and stamp.exists() and stamp.read_text().strip() == digest:
+        return str(lib)
+    extra = ["-DYART_BOUNDS_CHECK"] if bounds_check else []
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", str(lib)] + [str(CSRC / s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    (PKG / "build.log").write_text(" ".join(cmd) + "\n" + log)
+    (PKG / ("build_checked.log" if bounds_check else "build.log")).write_text(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed (see %s)" % (PKG / "build.log"))
     if verbose:
         print(log)
-    STAMP.write_text(digest)
-    return str(LIB)
+    stamp.write_text(digest)
+    return str(lib)
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, bounds_check="--bounds-check" in sys.argv))

@@ -109,12 +109,29 @@ YART_DEV F8 ldg256(const float4* p) {
 // ---------------------------------------------------------------------------------------------
 // Scene in HBM
 // ---------------------------------------------------------------------------------------------
+// Bounds-checked build (python -m build --bounds-check, tools/bounds_check.sh): every index a kernel forms
+// into the tree, the triangle records, the traversal stack and the ray / hit arrays is checked and a
+// violation traps (the next CUDA call of the context fails).  compute-sanitizer is not available on the
+// GPU pool this was developed on; this build takes its place.  Compiled out of the product library.
+#ifdef YART_BOUNDS_CHECK
+#define YART_CHECK(cond)                                                              \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      printf("YART_CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond);             \
+      __trap();                                                                       \
+    }                                                                                 \
+  } while (0)
+#else
+#define YART_CHECK(cond) ((void)0)
+#endif
+
 struct DevMesh {
   const float4* nodes;  // 8 float4 per node (host_common.h FlatNode: x, y, z slab pairs, children)
   const float4* tris;   // 3 float4 per triangle, tree order (FlatTri)
   const double* shade;  // 12 doubles per triangle (FlatTriShade: 9 normals + 6 float uvs)
   uint32_t root;
   uint32_t max_stack;
+  uint32_t n_nodes, n_tris;
   double bound[3];      // max |coordinate| per axis
 };
 

@@ -162,6 +162,7 @@ YART_DEV void prim_record(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
     }
     case YART_OBJ_MESH: { // the winning lane of an L4QBVH leaf (qbvh.rs:452-489)
       const DevMesh m = S.meshes[o.index];
+      YART_CHECK(prim < m.n_tris);
       const double* sh = m.shade + (size_t)prim * 12;
       const float* uvf = reinterpret_cast<const float*>(sh + 9);
       rec.p = d3(ro.x + t * rd.x, ro.y + t * rd.y, ro.z + t * rd.z);
@@ -513,6 +514,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams R, uint32_t* 
       const int leader = __ffs(ballot) - 1;
       if ((int)lane == leader) pos = atomicAdd(queue_count, (uint32_t)__popc(ballot));
       pos = __shfl_sync(0xffffffffu, pos, leader);
+      YART_CHECK(pos + __popc(ballot) <= R.n_pixels * R.spp_batch);
       if (alive) queue[pos + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)id;
     }
   }
@@ -559,7 +561,9 @@ __global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const Rend
       uint32_t my_id = YART_MISS, cls = 4;
       if (it < n) {
         my_id = queue[it];
+        YART_CHECK(my_id < R.n_pixels * R.spp_batch);
         const uint32_t obj = R.st.hits[my_id].obj;
+        YART_CHECK(obj == YART_MISS || obj < S.n_objects);
         cls = 0;
         if (obj != YART_MISS) {
           const uint32_t kind = S.materials[S.objects[obj].material].kind;
@@ -708,6 +712,7 @@ __global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const Rend
       const int leader = __ffs(ballot) - 1;
       if ((int)lane == leader) pos = atomicAdd(next_count, (uint32_t)__popc(ballot));
       pos = __shfl_sync(0xffffffffu, pos, leader);
+      YART_CHECK(pos + __popc(ballot) <= R.n_pixels * R.spp_batch);
       if (alive) next_queue[pos + __popc(ballot & ((1u << lane) - 1u))] = id;
     }
     __syncthreads(); // s_ids / s_cnt are rewritten by the next round

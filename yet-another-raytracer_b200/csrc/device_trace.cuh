@@ -156,6 +156,7 @@ YART_DEV bool group_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
     const uint32_t id = stack[--sp];
     if (id >> 31) {
       const uint32_t count = (id >> 27) & 0xF, first = id & 0x7FFFFFFu;
+      YART_CHECK(first + count <= g.n_members);
       for (uint32_t i = first; i < first + count; ++i) {
         double ti, bu, bv;
         uint32_t pr;
@@ -184,6 +185,7 @@ YART_DEV bool group_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
         tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
         t0 = ((double)lo[k][2] - ro.z) * iz; t1 = ((double)hi[k][2] - ro.z) * iz;
         tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
+        YART_CHECK(sp < 24 || !(tf >= tn));
         if (tf >= tn && sp < 24) stack[sp++] = cid[k];
       }
     }
@@ -237,7 +239,7 @@ struct PassCommon {
   uint64_t n_items;
   DevHit* hits;                // indexed by ray id: the closest hit so far
   uint32_t first_pass;         // 1: nothing recorded yet, start from t_max and always write
-  uint32_t _pad;
+  uint32_t n_rays;             // length of rays[] and hits[] (bounds-checked build)
   double t_min, t_max;
 };
 
@@ -251,6 +253,7 @@ struct TraverseParams {
   uint32_t refill_threshold;  // run the retire/fetch phase once this many lanes wait for it
   uint32_t node_threshold;    // leave the inner-node loop once fewer lanes than this are in it
   uint32_t _pad;
+  uint32_t n_nodes, n_tris;   // array lengths (bounds-checked build)
   double sin_theta, cos_theta, offset[3];
   double bound[3];            // max |coordinate| of the mesh per axis (for the f32 slab error bound)
   uint32_t* work_counter;     // zero before launch
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           exhausted = true;
         } else {
           ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
+          YART_CHECK(ray_id < P.c.n_rays);
           const yart_ray wr = P.c.rays[ray_id];
           t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
           D3 ro = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
@@ -455,6 +459,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
         if (lm != 0 || (uint32_t)__popc(wm) >= RT) break;
       }
       if (has_node) {
+        YART_CHECK(cur < P.n_nodes);
         const float4* nd = nodes + (size_t)cur * 8;
         // the whole 128-byte node in four 256-bit loads, all in flight together
         const F8 sx8 = ldg256(nd + 0), sy8 = ldg256(nd + 2), sz8 = ldg256(nd + 4), cm8 = ldg256(nd + 6);
@@ -541,6 +546,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           if (h2) s_stack[sp + br + (Rr ? 0u : h3)][tid] = ch.z;
           if (h3) s_stack[sp + br + (Rr ? h2 : 0u)][tid] = ch.w;
           sp += (int)(nl + nr);
+          YART_CHECK(sp <= STACK + 1);
         }
         if (sp == 0) {
           cur = kSentinel;
@@ -556,6 +562,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
       const uint32_t count = (cur >> 27) & 0xFu;
       const uint32_t first = cur & 0x7FFFFFFu;
       if (COUNT) n_tris += count;
+      YART_CHECK(count >= 1 && count <= 4 && first + count <= P.n_tris);
       for (uint32_t j = 0; j < count; ++j) {
         const uint32_t i = NEAR ? (count - 1u - j) : j;
         const float4* tp = tris + (size_t)(first + i) * 3;
@@ -605,6 +612,7 @@ __global__ void __launch_bounds__(256) k_analytic(const AnalyticParams P) {
   const uint64_t n = P.c.n_items_dev ? (uint64_t)*P.c.n_items_dev : P.c.n_items;
   for (uint64_t item = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; item < n; item += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
+    YART_CHECK(ray_id < P.c.n_rays);
     const yart_ray wr = P.c.rays[ray_id];
     const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
     const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);

@@ -358,6 +358,11 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       T.nodes = m.nodes;
       T.tris = m.tris;
       T.root = m.root;
+      T.n_nodes = m.n_nodes;
+      T.n_tris = m.n_tris;
+#ifdef YART_BOUNDS_CHECK
+      if (getenv("YART_FAULT_INJECT")) T.n_nodes = 1; // prove the checks are live (tests/test_gpu_bounds.py)
+#endif
       T.obj_index = i;
       T.wrap = o.wrap & (YART_WRAP_ROTATE_Y | YART_WRAP_TRANSLATE);
       T.refill_threshold = (uint32_t)std::max(1, std::min(32, rt));
@@ -566,6 +571,8 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
     meshes[i].shade = reinterpret_cast<const double*>(ds);
     meshes[i].root = q.root;
     meshes[i].max_stack = q.max_stack;
+    meshes[i].n_nodes = (uint32_t)q.nodes.size();
+    meshes[i].n_tris = (uint32_t)q.tris.size();
     for (int a = 0; a < 3; ++a) meshes[i].bound[a] = std::fmax(std::fabs(q.bbox_min[a]), std::fabs(q.bbox_max[a]));
     ctx->max_stack = std::max(ctx->max_stack, q.max_stack);
     memset(&solo[i], 0, sizeof(yart_object));
@@ -715,6 +722,7 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
   memset(&q, 0, sizeof(q));
   q.c.rays = d_rays;
   q.c.n_items = n;
+  q.c.n_rays = (uint32_t)n;
   q.c.hits = ctx->hits.as<DevHit>();
   q.c.t_min = t_min;
   q.c.t_max = t_max;
@@ -868,6 +876,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
           q.c.rays = R.st.rays;
           q.c.queue = qa;
           q.c.n_items_dev = counts + b;
+          q.c.n_rays = R.n_pixels * spp;
           q.c.hits = R.st.hits;
           q.c.t_min = 0.001; // world.hit(ray_in, 0.001, f64::INFINITY) (main.rs:548)
           q.c.t_max = INFINITY;
