@@ -118,6 +118,28 @@ def test_render_is_deterministic_and_sample_ranges_add_up(yart, orc, ctx):
     assert not np.array_equal(other, full)
 
 
+def test_full_size_frame_matches_oracle_and_batches_add_up(yart, orc, ctx):
+    """BASELINE.json config 3 at its real frame (david, 1920x1080, depth 50), two samples per pixel against the
+    oracle on every pixel; then the size-independent property at a sample count that spans two device batches
+    (32 spp per batch at this frame): film[0,34) == film[0,32) chained with [32,34), bit for bit."""
+    preset = yart.ScenePreset("david")
+    s = orc.Scene(preset)
+    ctx.set_scene(preset)
+    w, h = 1920, 1080
+    cam = preset.camera(w, h)
+    want, st_w = s.render(cam, w, h, 5, 7, max_depth=50, seed=3, n_threads=os.cpu_count())
+    got, st = ctx.render(cam, w, h, 5, 7, max_depth=50, seed=3)
+    compare_films(got, want, "david 1920x1080", 0.9995)
+    assert st.paths == st_w.paths == w * h * 2
+    assert abs(int(st.rays) - int(st_w.rays)) <= 64
+    whole, st34 = ctx.render(cam, w, h, 0, 34, max_depth=50, seed=3)
+    part, _ = ctx.render(cam, w, h, 0, 32, max_depth=50, seed=3)
+    part, _ = ctx.render(cam, w, h, 32, 34, max_depth=50, seed=3, film=part)
+    assert np.array_equal(whole, part)
+    # SURVEY Appendix B measured ~4.3 rays / sample on square frames; 16:9 sees more background (~3.6)
+    assert st34.paths == w * h * 34 and 3.2 < st34.rays / st34.paths < 4.6
+
+
 def test_non_multiple_of_8_frames_follow_the_reference_tiling(yart, orc, ctx):
     preset = yart.ScenePreset("cornell-box")
     s = orc.Scene(preset)
