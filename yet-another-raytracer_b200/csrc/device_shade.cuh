@@ -436,6 +436,10 @@ struct RenderParams {
   uint32_t pixel_base, n_pixels; // this batch covers pixels [pixel_base, pixel_base + n_pixels)
   uint32_t sample_base, spp_batch;
   uint32_t max_depth;
+  // objects [tail_begin, tail_end) of the world list -- a trailing run of plain spheres -- are intersected by
+  // k_shade itself (it has the ray and the hit in hand) instead of costing a pass over the queue
+  uint32_t tail_begin, tail_end;
+  uint32_t _pad;
   uint64_t seed;
 };
 
@@ -562,7 +566,27 @@ __global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const Rend
       if (it < n) {
         my_id = queue[it];
         YART_CHECK(my_id < R.n_pixels * R.spp_batch);
-        const uint32_t obj = R.st.hits[my_id].obj;
+        uint32_t obj = R.st.hits[my_id].obj;
+        if (R.tail_end > R.tail_begin) {
+          // the last objects of HittableList::hit's scan (hittable.rs:66-79), same calls as k_analytic makes
+          const yart_ray wr = R.st.rays[my_id];
+          const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
+          const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+          double t_best = R.st.hits[my_id].t; // (+inf on a miss; t_max of the scan is +inf, main.rs:548)
+          bool changed = false;
+          for (uint32_t oi = R.tail_begin; oi < R.tail_end; ++oi) {
+            const yart_object& so = S.objects[oi];
+            double t;
+            if (sphere_t(d3(so.p[0], so.p[1], so.p[2]), so.p[3], wo, wd, 0.001, t_best, t)) {
+              t_best = t; obj = oi; changed = true;
+            }
+          }
+          if (changed) {
+            DevHit h;
+            h.t = t_best; h.bu = 0.0; h.bv = 0.0; h.obj = obj; h.prim = 0;
+            R.st.hits[my_id] = h; // read back by whichever thread shades this path (after the barrier below)
+          }
+        }
         YART_CHECK(obj == YART_MISS || obj < S.n_objects);
         cls = 0;
         if (obj != YART_MISS) {

@@ -784,6 +784,18 @@ static int fill_render_params(yart_ctx* ctx, const yart_camera* cam, const yart_
   R.height = o->height;
   R.max_depth = o->max_depth;
   R.seed = o->seed;
+  {
+    // A trailing run of plain spheres that directly follows a mesh pass is intersected inside k_shade (which
+    // reads the ray and the hit anyway) -- saves one read-modify-write pass over the queue per bounce.
+    static const int fold = tune_env("YART_TUNE_FOLD_TAIL", 1);
+    const uint32_t n_obj = ctx->scene.n_objects;
+    uint32_t tb = n_obj;
+    while (tb > 0 && ctx->h_objects[tb - 1].kind == YART_OBJ_SPHERE && ctx->h_objects[tb - 1].wrap == 0) tb--;
+    const bool after_mesh = tb > 0 && ctx->h_objects[tb - 1].kind == YART_OBJ_MESH && !(ctx->h_objects[tb - 1].wrap & YART_WRAP_MEDIUM);
+    if (!fold || !after_mesh || n_obj - tb > 16) tb = n_obj;
+    R.tail_begin = tb;
+    R.tail_end = n_obj;
+  }
   return YART_OK;
 }
 
@@ -882,7 +894,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
           q.c.t_max = INFINITY;
           q.d_objects = ctx->scene.objects;
           q.h_objects = ctx->h_objects.data();
-          q.n_objects = ctx->scene.n_objects;
+          q.n_objects = R.tail_begin; // (== n_objects unless k_shade takes a trailing run of spheres)
           q.ray_time = R.st.time;
           q.seed = o->seed;
           q.bounce = b;
