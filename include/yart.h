@@ -278,6 +278,7 @@ int yart_qbvh_get_info(const yart_qbvh* q, yart_qbvh_info* out);
  * tris = n_tris x 12 x 4 bytes in tree order.  Borrowed, valid until free. */
 const void* yart_qbvh_nodes(const yart_qbvh* q);
 const void* yart_qbvh_tris(const yart_qbvh* q);
+const void* yart_qbvh_shade(const yart_qbvh* q); /* n_tris x 96 bytes: vertex normals (f64) + uvs (f32), tree order */
 
 /* build_scene_preset (main.rs:211-432) + scenes.rs.  `name` is the reference's kebab-case
  * --scene value (main.rs:61-76).  `assets_dir` holds cube.obj / david.obj / sycee.obj /
@@ -317,7 +318,17 @@ const char* yart_last_error(const yart_ctx* ctx);
 int yart_ctx_set_stream(yart_ctx* ctx, void* cuda_stream);
 int yart_ctx_synchronize(yart_ctx* ctx);
 
-/* Builds the QBVH of every mesh (host), flattens and uploads everything.  Replaces the
+/* Which L4QBVH builder yart_ctx_set_scene uses for the meshes.  Both give the same tree byte for byte
+ * (qbvh.rs:251-361); with YART_BUILDER_DEVICE the sorts run on the GPU and the tree never visits the host. */
+#define YART_BUILDER_HOST 0u
+#define YART_BUILDER_DEVICE 1u
+int yart_ctx_set_builder(yart_ctx* ctx, uint32_t builder);
+
+/* L4QBVH::new on the GPU of `ctx`, copied back into a yart_qbvh so that yart_qbvh_get_info / _nodes / _tris
+ * (and a comparison with yart_qbvh_build) work on it. */
+int yart_qbvh_build_device(yart_ctx* ctx, const yart_trimesh* mesh, yart_qbvh** out);
+
+/* Builds the QBVH of every mesh (see yart_ctx_set_builder), flattens and uploads everything.  Replaces the
  * construction of `world: Arc<HittableList>` + `lights` (main.rs:434-446). */
 int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* scene);
 

@@ -175,3 +175,29 @@ def test_cli_writes_a_png(yart, tmp_path):
     assert im.size == (64, 64) and im.mode == "RGBA"
     px = np.asarray(im)
     assert (px[..., 3] == 255).all() and px[..., :3].mean() > 5
+
+
+def test_cli_preview_checkpoint_and_resume_reproduce_the_one_shot_image(yart, tmp_path):
+    """progressive preview and checkpoint / resume.  A render cut at 3 of 6 samples and
+    resumed, and one that wrote previews every 2 samples, give the same bytes as the uninterrupted render."""
+    import importlib
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    cli = importlib.import_module("yart_cli")
+    from PIL import Image
+    base = ["--scene", "cornell-box", "--width", "48", "--seed", "5"]
+    one, prog, res = (str(tmp_path / n) for n in ("one.png", "prog.png", "res.png"))
+    ck = str(tmp_path / "ck.npz")
+    assert cli.main(base + ["--samples", "6", "--output", one]) == 0
+    assert cli.main(base + ["--samples", "6", "--output", prog, "--preview-every", "2"]) == 0
+    assert cli.main(base + ["--samples", "3", "--output", res, "--checkpoint", ck]) == 0
+    half = np.asarray(Image.open(res)).copy()
+    with np.load(ck) as z:
+        assert int(z["samples_done"]) == 3 and z["film"].shape == (48, 48, 3)
+    assert cli.main(base + ["--samples", "6", "--output", res, "--checkpoint", ck, "--resume"]) == 0
+    a, b, c = (np.asarray(Image.open(p)) for p in (one, prog, res))
+    assert np.array_equal(a, b) and np.array_equal(a, c) and not np.array_equal(a, half)
+    with pytest.raises(SystemExit):  # a checkpoint of another image is refused
+        cli.main(["--scene", "cornell-box", "--width", "48", "--seed", "6", "--samples", "6", "--output", res,
+                  "--checkpoint", ck, "--resume"])

@@ -3,11 +3,18 @@
 
     python yart_cli.py --scene david [--output out.png] [--width W] [--height H] [--samples N]
                        [--max-depth D] [--vfov F] [--aperture A]            (reference flags)
-                       [--seed S] [--gpus G] [--order near|reference]        (additions)
+                       [--seed S] [--order near|reference] [--device D]      (additions)
+                       [--preview-every N] [--checkpoint FILE] [--resume]    (additions)
 
 `--workers` is accepted for compatibility and ignored (the render runs on the GPU).  Option resolution
 follows resolve_render_options / resolve_dimensions (main.rs:166-209); the image is finalised exactly like
 main.rs:710-718 and written as PNG (main.rs:769-774).  There is no CPU mode.
+
+Progressive output and checkpoints rest on one property of yart_render (tests/test_gpu_render.py): the film is
+the per-pixel SUM of samples added in sample order, so rendering [0, a) and then [a, b) into the same film is
+bit-identical to rendering [0, b) at once.  `--preview-every N` writes the PNG of what exists after every N
+samples per pixel; `--checkpoint FILE` stores (film, samples done, the options that define the image) as .npz at
+the same moments; `--resume` continues from FILE if it matches the request.
 """
 import argparse
 import importlib
@@ -45,7 +52,42 @@ def build_parser(scene_names):
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--order", choices=["near", "reference"], default="near")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--preview-every", type=positive_int, default=None, dest="preview_every",
+                    help="write the image after every N samples per pixel")
+    ap.add_argument("--checkpoint", default=None, help=".npz file holding the film and the samples done so far")
+    ap.add_argument("--resume", action="store_true", help="continue from --checkpoint if it matches this render")
     return ap
+
+
+def _identity(args, o):
+    """Everything that decides what sample k of pixel p is; a checkpoint is only valid for the same values."""
+    return [args.scene, int(o["width"]), int(o["height"]), int(o["max_depth"]), float(o["vfov"]), float(o["aperture"]),
+            int(args.seed)]
+
+
+def save_checkpoint(path, film, done, ident):
+    import json
+    import numpy as np
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, film=film, samples_done=np.int64(done), identity=np.array(json.dumps(ident)))
+    os.replace(tmp, path)  # a kill during the write leaves the previous checkpoint intact
+
+
+def load_checkpoint(path, ident):
+    import json
+    import numpy as np
+    with np.load(path) as z:
+        if json.loads(str(z["identity"])) != ident:
+            raise SystemExit("checkpoint %s was made with other options: %s" % (path, str(z["identity"])))
+        return np.ascontiguousarray(z["film"]), int(z["samples_done"])
+
+
+def write_png(ctx, film, spp_done, path):
+    parent = os.path.dirname(path)
+    if parent:
+        os.makedirs(parent, exist_ok=True)
+    from PIL import Image
+    Image.fromarray(ctx.film_finalize(film, spp_done), "RGBA").save(path)
 
 
 def main(argv=None):
@@ -59,15 +101,33 @@ def main(argv=None):
     ctx.set_scene(preset)
     cam = preset.camera(o["width"], o["height"], o["vfov"], o["aperture"])
     order = y.ORDER_NEAR if args.order == "near" else y.ORDER_REFERENCE
-    film, st = ctx.render(cam, o["width"], o["height"], 0, o["samples_per_pixel"], o["max_depth"], args.seed, order)
-    rgba = ctx.film_finalize(film, o["samples_per_pixel"])
+    total = o["samples_per_pixel"]
+    ident = _identity(args, o)
+    film, done = None, 0
+    if args.resume:
+        if not args.checkpoint:
+            raise SystemExit("--resume needs --checkpoint FILE")
+        if os.path.exists(args.checkpoint):
+            film, done = load_checkpoint(args.checkpoint, ident)
+            done = min(done, total)
+            print("resuming %s at %d of %d samples per pixel" % (args.checkpoint, done, total))
+    step = args.preview_every or total
+    paths = rays = 0
+    gpu_ms = 0.0
+    while done < total:
+        nxt = min(total, done + step)
+        film, st = ctx.render(cam, o["width"], o["height"], done, nxt, o["max_depth"], args.seed, order, film=film)
+        paths, rays, gpu_ms, done = paths + st.paths, rays + st.rays, gpu_ms + st.gpu_ms, nxt
+        if done < total or args.checkpoint:
+            if args.checkpoint:
+                save_checkpoint(args.checkpoint, film, done, ident)
+            if done < total:
+                write_png(ctx, film, done, o["output_path"])  # normalised by the samples that exist so far
+    if film is None:  # (resumed a finished render)
+        raise SystemExit("nothing to do")
+    write_png(ctx, film, total, o["output_path"])
     print("%s rendered in %d seconds" % (o["output_path"], int(time.time() - start)))  # main.rs:763-767
-    print("  %d paths, %d rays, %.1f Mrays/s on the device" % (st.paths, st.rays, st.rays / max(st.gpu_ms, 1e-9) / 1e3))
-    parent = os.path.dirname(o["output_path"])
-    if parent:
-        os.makedirs(parent, exist_ok=True)
-    from PIL import Image
-    Image.fromarray(rgba, "RGBA").save(o["output_path"])
+    print("  %d paths, %d rays, %.1f Mrays/s on the device" % (paths, rays, rays / max(gpu_ms, 1e-9) / 1e3))
     return 0
 
 

@@ -29,6 +29,9 @@ SCENE_NAMES = ["random-scene", "two-spheres", "two-perlin-spheres", "earth", "si
                "cornell-box-smoke", "next-week-final", "teapot", "bunny", "three-spheres", "sycee", "david"]
 
 
+BUILDER_HOST, BUILDER_DEVICE = 0, 1
+
+
 class YartError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("yart error %d: %s" % (code, message))
@@ -60,6 +63,9 @@ def load_library():
         "yart_qbvh_get_info": (i32, [vp, P(abi.QbvhInfo)]),
         "yart_qbvh_nodes": (vp, [vp]),
         "yart_qbvh_tris": (vp, [vp]),
+        "yart_qbvh_shade": (vp, [vp]),
+        "yart_qbvh_build_device": (i32, [vp, P(abi.Trimesh), P(vp)]),
+        "yart_ctx_set_builder": (i32, [vp, u32]),
         "yart_preset_build": (i32, [C.c_char_p, C.c_char_p, u64, P(vp)]),
         "yart_preset_free": (None, [vp]),
         "yart_preset_scene": (P(abi.SceneDesc), [vp]),
@@ -94,7 +100,8 @@ EXPORTED_SYMBOLS = [
     "yart_preset_free", "yart_preset_scene", "yart_preset_get_info", "yart_preset_count", "yart_preset_name",
     "yart_resolve_dimensions", "yart_preset_camera", "yart_device_count", "yart_ctx_create", "yart_ctx_destroy",
     "yart_last_error", "yart_ctx_set_stream", "yart_ctx_synchronize", "yart_ctx_set_scene", "yart_closest_hit",
-    "yart_render", "yart_film_finalize", "yart_generate_camera_rays",
+    "yart_render", "yart_film_finalize", "yart_generate_camera_rays", "yart_qbvh_shade", "yart_qbvh_build_device",
+    "yart_ctx_set_builder",
 ]
 
 
@@ -155,19 +162,43 @@ class TriangleMesh:
             self._h = None
 
 
+def trimesh_from_arrays(positions, normals=None, uvs=None):
+    """A yart_trimesh view of numpy arrays ((n,3,3) f32 positions, (n,3,3) f64 normals, (n,3,2) f32 uvs).
+    Returns (trimesh, keepalive): pass keepalive wherever the view is used."""
+    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3, 3)
+    n = pos.shape[0]
+    nrm = np.ascontiguousarray(np.zeros((n, 3, 3)) if normals is None else normals, dtype=np.float64).reshape(n, 3, 3)
+    uv = np.ascontiguousarray(np.zeros((n, 3, 2)) if uvs is None else uvs, dtype=np.float32).reshape(n, 3, 2)
+    t = abi.Trimesh()
+    t.n_tris = n
+    t.positions = pos.ctypes.data_as(C.POINTER(C.c_float))
+    t.normals = nrm.ctypes.data_as(C.POINTER(C.c_double))
+    t.uvs = uv.ctypes.data_as(C.POINTER(C.c_float))
+    return t, (pos, nrm, uv)
+
+
 class L4QBVH:
     """`L4QBVH::new` (reference qbvh.rs:251-361), flattened into the device layout."""
 
-    def __init__(self, trimesh, keepalive=None):
+    def __init__(self, trimesh, keepalive=None, ctx=None):
+        """ctx=None: the host builder; ctx=Context: the GPU builder (same tree, byte for byte)."""
         self._keep = keepalive
         self._h = C.c_void_p()
-        _check_global(load_library().yart_qbvh_build(C.byref(trimesh), C.byref(self._h)))
+        if ctx is None:
+            _check_global(load_library().yart_qbvh_build(C.byref(trimesh), C.byref(self._h)))
+        else:
+            ctx._check(load_library().yart_qbvh_build_device(ctx._h, C.byref(trimesh), C.byref(self._h)))
         self.info = abi.QbvhInfo()
         _check_global(_lib.yart_qbvh_get_info(self._h, C.byref(self.info)))
 
     @classmethod
-    def from_mesh(cls, mesh):
-        return cls(mesh.trimesh, keepalive=mesh)
+    def from_mesh(cls, mesh, ctx=None):
+        return cls(mesh.trimesh, keepalive=mesh, ctx=ctx)
+
+    def shade(self):
+        n = self.info.n_tris
+        buf = (C.c_char * (n * 96)).from_address(_lib.yart_qbvh_shade(self._h))
+        return np.frombuffer(buf, dtype=np.uint8, count=n * 96).reshape(n, 96).copy()
 
     def nodes(self):
         n = self.info.n_nodes
@@ -253,6 +284,10 @@ class Context:
         desc = scene.desc if isinstance(scene, ScenePreset) else scene
         self._scene_keep = scene
         self._check(_lib.yart_ctx_set_scene(self._h, desc))
+
+    def set_builder(self, builder):
+        """BUILDER_HOST (default) or BUILDER_DEVICE: which L4QBVH builder set_scene uses for meshes."""
+        self._check(_lib.yart_ctx_set_builder(self._h, builder))
 
     def set_stream(self, cuda_stream_ptr):
         self._check(_lib.yart_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))

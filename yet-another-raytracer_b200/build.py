@@ -28,8 +28,8 @@ LIB = PKG / "libyart_b200.so"
 LIB_CHECKED = PKG / "libyart_b200_checked.so"
 STAMP = PKG / ".build_stamp"
 
-SOURCES = ["host_obj.cpp", "host_qbvh.cpp", "host_presets.cpp", "host_api.cpp", "yart_device.cu"]
-HEADERS = ["host_common.h", "device_common.cuh", "device_trace.cuh", "device_shade.cuh"]
+SOURCES = ["host_obj.cpp", "host_qbvh.cpp", "host_presets.cpp", "host_api.cpp", "yart_device.cu", "device_build.cu"]
+HEADERS = ["host_common.h", "device_common.cuh", "device_trace.cuh", "device_shade.cuh", "device_build.h"]
 INCLUDES = ["yart.h", "yart_rng.h", "yart_spectral_tables.h"]
 
 NVCC_FLAGS = [

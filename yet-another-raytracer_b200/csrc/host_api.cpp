@@ -9,10 +9,6 @@
 struct yart_objfile {
   yart::TriSoup soup;
 };
-struct yart_qbvh {
-  yart::FlatQbvh q;
-  uint32_t n_tris;
-};
 struct yart_preset {
   yart::Preset p;
 };
@@ -86,6 +82,7 @@ int yart_qbvh_get_info(const yart_qbvh* q, yart_qbvh_info* out) {
 }
 const void* yart_qbvh_nodes(const yart_qbvh* q) { return q ? q->q.nodes.data() : nullptr; }
 const void* yart_qbvh_tris(const yart_qbvh* q) { return q ? q->q.tris.data() : nullptr; }
+const void* yart_qbvh_shade(const yart_qbvh* q) { return q ? q->q.shade.data() : nullptr; }
 
 int yart_preset_build(const char* name, const char* assets_dir, uint64_t seed, yart_preset** out) {
   if (!name || !assets_dir || !out) {

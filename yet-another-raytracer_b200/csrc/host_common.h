@@ -108,3 +108,9 @@ void camera_for(const yart_preset_info& info, uint32_t width, uint32_t height, d
                 yart_camera* out);
 
 } // namespace yart
+
+// the opaque handle of include/yart.h (host_api.cpp and yart_device.cu both create it)
+struct yart_qbvh {
+  yart::FlatQbvh q;
+  uint32_t n_tris;
+};

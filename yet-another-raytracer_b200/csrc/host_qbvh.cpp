@@ -133,12 +133,15 @@ struct Builder {
     FlatNode nd;
     for (int k = 0; k < 4; ++k) {
       const bool s = bx[k].some;
-      nd.min_x[k] = s ? bx[k].mn[0] : FLT_MAX;
-      nd.min_y[k] = s ? bx[k].mn[1] : FLT_MAX;
-      nd.min_z[k] = s ? bx[k].mn[2] : FLT_MAX;
-      nd.max_x[k] = s ? bx[k].mx[0] : FLT_MAX;
-      nd.max_y[k] = s ? bx[k].mx[1] : FLT_MAX;
-      nd.max_z[k] = s ? bx[k].mx[2] : FLT_MAX;
+      // (+ 0.0f turns a -0.0 plane into +0.0: which of two equal zeros a min/max fold keeps depends on the
+      // fold order, and no slab test can tell them apart; this makes the stored tree canonical, so the GPU
+      // builder -- another fold order -- produces the same bytes)
+      nd.min_x[k] = s ? bx[k].mn[0] + 0.0f : FLT_MAX;
+      nd.min_y[k] = s ? bx[k].mn[1] + 0.0f : FLT_MAX;
+      nd.min_z[k] = s ? bx[k].mn[2] + 0.0f : FLT_MAX;
+      nd.max_x[k] = s ? bx[k].mx[0] + 0.0f : FLT_MAX;
+      nd.max_y[k] = s ? bx[k].mx[1] + 0.0f : FLT_MAX;
+      nd.max_z[k] = s ? bx[k].mx[2] + 0.0f : FLT_MAX;
       nd.child[k] = ids[k];
     }
     nd.axes = top | (la << 2) | (ra << 4);
@@ -175,8 +178,8 @@ bool build_qbvh(const yart_trimesh& mesh, FlatQbvh& out, std::string& err) {
   out.height = height;
   out.max_stack = 3 * height + 1;
   for (int a = 0; a < 3; ++a) {
-    out.bbox_min[a] = (double)box.mn[a];
-    out.bbox_max[a] = (double)box.mx[a];
+    out.bbox_min[a] = (double)(box.mn[a] + 0.0f);
+    out.bbox_max[a] = (double)(box.mx[a] + 0.0f);
   }
   out.tris.resize(mesh.n_tris);
   out.shade.resize(mesh.n_tris);

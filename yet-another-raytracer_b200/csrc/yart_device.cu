@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/yart_spectral_tables.h"
+#include "device_build.h"
 #include "device_shade.cuh"
 #include "host_common.h"
 
@@ -227,6 +228,7 @@ struct yart_ctx {
   uint32_t n_meshes = 0;
   uint32_t max_stack = 0;
   bool has_media = false;
+  uint32_t builder = YART_BUILDER_HOST;
   double* d_cie = nullptr;
   double* d_smits = nullptr;
 
@@ -495,6 +497,54 @@ int yart_ctx_set_stream(yart_ctx* ctx, void* cuda_stream) {
   return YART_OK;
 }
 
+int yart_ctx_set_builder(yart_ctx* ctx, uint32_t builder) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (builder > YART_BUILDER_DEVICE) {
+    ctx->err = "yart_ctx_set_builder: unknown builder";
+    return YART_ERR_INVALID;
+  }
+  ctx->builder = builder;
+  return YART_OK;
+}
+
+int yart_qbvh_build_device(yart_ctx* ctx, const yart_trimesh* mesh, yart_qbvh** out) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!mesh || !out) {
+    ctx->err = "yart_qbvh_build_device: null argument";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  DeviceQbvh dq;
+  std::string err;
+  if (!build_qbvh_device(ctx->stream, *mesh, dq, err)) {
+    ctx->err = "yart_qbvh_build_device: " + err;
+    return err.find("cuda") != std::string::npos ? YART_ERR_CUDA : YART_ERR_INVALID;
+  }
+  yart_qbvh* q = new (std::nothrow) yart_qbvh();
+  if (!q) {
+    free_qbvh_device(dq);
+    return YART_ERR_NOMEM;
+  }
+  q->q.nodes.resize(dq.n_nodes);
+  q->q.tris.resize(dq.n_tris);
+  q->q.shade.resize(dq.n_tris);
+  cudaError_t e = cudaMemcpyAsync(q->q.nodes.data(), dq.nodes, (size_t)dq.n_nodes * sizeof(FlatNode), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(q->q.tris.data(), dq.tris, (size_t)dq.n_tris * sizeof(FlatTri), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(q->q.shade.data(), dq.shade, (size_t)dq.n_tris * sizeof(FlatTriShade), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  q->q.root = dq.root; q->q.n_leaves = dq.n_leaves; q->q.height = dq.height; q->q.max_stack = dq.max_stack;
+  for (int a = 0; a < 3; ++a) { q->q.bbox_min[a] = dq.bbox_min[a]; q->q.bbox_max[a] = dq.bbox_max[a]; }
+  q->n_tris = dq.n_tris;
+  free_qbvh_device(dq);
+  if (e != cudaSuccess) {
+    delete q;
+    ctx->err = std::string("yart_qbvh_build_device: copy back: ") + cudaGetErrorString(e);
+    return YART_ERR_CUDA;
+  }
+  *out = q;
+  return YART_OK;
+}
+
 int yart_ctx_synchronize(yart_ctx* ctx) {
   if (!ctx) return YART_ERR_INVALID;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -549,30 +599,48 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
   std::vector<yart_object> solo(d->n_meshes);
   ctx->max_stack = 0;
   for (uint32_t i = 0; i < d->n_meshes; ++i) {
-    FlatQbvh q;
-    std::string err;
-    if (!build_qbvh(d->meshes[i], q, err)) {
-      ctx->err = "yart_ctx_set_scene: mesh " + std::to_string(i) + ": " + err;
-      ctx->free_scene();
-      return YART_ERR_INVALID;
-    }
+    struct { uint32_t root, max_stack, n_nodes, n_tris; double bbox_min[3], bbox_max[3]; } q;
     FlatNode* dn;
     FlatTri* dt;
     FlatTriShade* ds;
-    int rc;
-    if ((rc = upload(ctx, q.nodes.data(), q.nodes.size(), &dn)) || (rc = upload(ctx, q.tris.data(), q.tris.size(), &dt)) ||
-        (rc = upload(ctx, q.shade.data(), q.shade.size(), &ds))) {
-      ctx->free_scene();
-      return rc;
+    std::string err;
+    if (ctx->builder == YART_BUILDER_DEVICE) {
+      DeviceQbvh dq;
+      if (!build_qbvh_device(ctx->stream, d->meshes[i], dq, err)) {
+        ctx->err = "yart_ctx_set_scene: mesh " + std::to_string(i) + " (device build): " + err;
+        ctx->free_scene();
+        return err.find("cuda") != std::string::npos ? YART_ERR_CUDA : YART_ERR_INVALID;
+      }
+      dn = dq.nodes; dt = dq.tris; ds = dq.shade;
+      ctx->scene_allocs.push_back(dn);
+      ctx->scene_allocs.push_back(dt);
+      ctx->scene_allocs.push_back(ds);
+      q.root = dq.root; q.max_stack = dq.max_stack; q.n_nodes = dq.n_nodes; q.n_tris = dq.n_tris;
+      for (int a = 0; a < 3; ++a) { q.bbox_min[a] = dq.bbox_min[a]; q.bbox_max[a] = dq.bbox_max[a]; }
+    } else {
+      FlatQbvh hq;
+      if (!build_qbvh(d->meshes[i], hq, err)) {
+        ctx->err = "yart_ctx_set_scene: mesh " + std::to_string(i) + ": " + err;
+        ctx->free_scene();
+        return YART_ERR_INVALID;
+      }
+      int rc;
+      if ((rc = upload(ctx, hq.nodes.data(), hq.nodes.size(), &dn)) || (rc = upload(ctx, hq.tris.data(), hq.tris.size(), &dt)) ||
+          (rc = upload(ctx, hq.shade.data(), hq.shade.size(), &ds))) {
+        ctx->free_scene();
+        return rc;
+      }
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // hq goes out of scope
+      q.root = hq.root; q.max_stack = hq.max_stack; q.n_nodes = (uint32_t)hq.nodes.size(); q.n_tris = (uint32_t)hq.tris.size();
+      for (int a = 0; a < 3; ++a) { q.bbox_min[a] = hq.bbox_min[a]; q.bbox_max[a] = hq.bbox_max[a]; }
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // q goes out of scope
     meshes[i].nodes = reinterpret_cast<const float4*>(dn);
     meshes[i].tris = reinterpret_cast<const float4*>(dt);
     meshes[i].shade = reinterpret_cast<const double*>(ds);
     meshes[i].root = q.root;
     meshes[i].max_stack = q.max_stack;
-    meshes[i].n_nodes = (uint32_t)q.nodes.size();
-    meshes[i].n_tris = (uint32_t)q.tris.size();
+    meshes[i].n_nodes = q.n_nodes;
+    meshes[i].n_tris = q.n_tris;
     for (int a = 0; a < 3; ++a) meshes[i].bound[a] = std::fmax(std::fabs(q.bbox_min[a]), std::fabs(q.bbox_max[a]));
     ctx->max_stack = std::max(ctx->max_stack, q.max_stack);
     memset(&solo[i], 0, sizeof(yart_object));
