@@ -319,7 +319,8 @@ int yart_ctx_set_stream(yart_ctx* ctx, void* cuda_stream);
 int yart_ctx_synchronize(yart_ctx* ctx);
 
 /* Which L4QBVH builder yart_ctx_set_scene uses for the meshes.  Both give the same tree byte for byte
- * (qbvh.rs:251-361); with YART_BUILDER_DEVICE the sorts run on the GPU and the tree never visits the host. */
+ * (qbvh.rs:251-361); with YART_BUILDER_DEVICE (the default) the sorts run on the GPU and the tree never visits
+ * the host. */
 #define YART_BUILDER_HOST 0u
 #define YART_BUILDER_DEVICE 1u
 int yart_ctx_set_builder(yart_ctx* ctx, uint32_t builder);

@@ -59,7 +59,7 @@ def test_scene_built_on_the_device_traces_identically(yart, orc, ctx, assets):
         hits_d, _ = ctx.closest_hit(rays, yart.TARGET_WORLD, 0.001, float("inf"), yart.ORDER_NEAR)
         film_d, _ = ctx.render(cam, 64, 48, 0, 4, seed=2)
     finally:
-        ctx.set_builder(yart.BUILDER_HOST)
+        ctx.set_builder(yart.BUILDER_DEVICE)  # the default
     assert hits_h.tobytes() == hits_d.tobytes() and np.array_equal(film_h, film_d)
 
 

@@ -286,7 +286,7 @@ class Context:
         self._check(_lib.yart_ctx_set_scene(self._h, desc))
 
     def set_builder(self, builder):
-        """BUILDER_HOST (default) or BUILDER_DEVICE: which L4QBVH builder set_scene uses for meshes."""
+        """BUILDER_DEVICE (default) or BUILDER_HOST: which L4QBVH builder set_scene uses for meshes."""
         self._check(_lib.yart_ctx_set_builder(self._h, builder))
 
     def set_stream(self, cuda_stream_ptr):

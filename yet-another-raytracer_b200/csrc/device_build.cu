@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -274,18 +275,23 @@ __global__ void k_node_boxes(const uint32_t* __restrict__ ids, uint32_t n_ids, c
   }
 }
 
-struct Scratch { // freed on every exit path
-  std::vector<void*> ptrs;
-  ~Scratch() {
-    for (void* p : ptrs) cudaFree(p);
-  }
+// One device allocation carved into the work arrays (a cudaMalloc per array costs more than the whole
+// build of a small mesh); freed on every exit path.
+struct Scratch {
+  size_t total = 0;
+  unsigned char* base = nullptr;
+  std::vector<std::pair<void**, size_t>> wants;
+  ~Scratch() { cudaFree(base); }
   template <class T>
-  cudaError_t alloc(T** out, size_t count) {
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(p);
-    *out = reinterpret_cast<T*>(p);
-    return e;
+  void want(T** out, size_t count) {
+    wants.push_back({reinterpret_cast<void**>(out), total});
+    total += (((count ? count : 1) * sizeof(T)) + 255) & ~(size_t)255;
+  }
+  cudaError_t commit() {
+    cudaError_t e = cudaMalloc((void**)&base, total ? total : 256);
+    if (e != cudaSuccess) return e;
+    for (auto& w : wants) *w.first = base + w.second;
+    return cudaSuccess;
   }
 };
 
@@ -329,34 +335,37 @@ bool build_qbvh_device(cudaStream_t stream, const yart_trimesh& mesh, DeviceQbvh
   int* d_seg_of_pos;
   Seg* d_segs;
   TopoNode* d_topo;
-  BUILD_TRY(scratch.alloc(&d_pos, (size_t)n * 9));
-  BUILD_TRY(scratch.alloc(&d_nrm, (size_t)n * 9));
-  BUILD_TRY(scratch.alloc(&d_uv, (size_t)n * 6));
-  BUILD_TRY(scratch.alloc(&d_bmin, (size_t)n * 3));
-  BUILD_TRY(scratch.alloc(&d_bmax, (size_t)n * 3));
-  BUILD_TRY(scratch.alloc(&d_cen, (size_t)n * 3));
-  BUILD_TRY(scratch.alloc(&d_perm, n));
-  BUILD_TRY(scratch.alloc(&d_perm2, n));
-  BUILD_TRY(scratch.alloc(&d_place, n));
-  BUILD_TRY(scratch.alloc(&d_place_sorted, n));
-  BUILD_TRY(scratch.alloc(&d_place_sorted2, n));
-  BUILD_TRY(scratch.alloc(&d_iota, n));
-  BUILD_TRY(scratch.alloc(&d_vals, n));
-  BUILD_TRY(scratch.alloc(&d_cen_key, n));
-  BUILD_TRY(scratch.alloc(&d_cen_key2, n));
-  BUILD_TRY(scratch.alloc(&d_seg_of_pos, n));
-  BUILD_TRY(scratch.alloc(&d_segs, total_segs));
-  BUILD_TRY(scratch.alloc(&d_bounds, max_segs * 6));
-  BUILD_TRY(scratch.alloc(&d_seg_axis, max_segs));
-  BUILD_TRY(scratch.alloc(&d_node_axes, n_nodes));
-  BUILD_TRY(scratch.alloc(&d_topo, n_nodes));
-  BUILD_TRY(scratch.alloc(&d_ids, n_nodes));
-  size_t tmp_a = 0, tmp_b = 0;
+  size_t tmp_a = 0, tmp_b = 0; // (sizing calls: no work is done, the pointers are not touched)
+  d_cen_key = d_cen_key2 = nullptr;
+  d_iota = d_vals = d_place_sorted = d_place_sorted2 = d_perm2 = nullptr;
   BUILD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_a, d_cen_key, d_cen_key2, d_iota, d_vals, (int)n, 0, 64, stream));
   BUILD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_b, d_place_sorted, d_place_sorted2, d_vals, d_perm2, (int)n, 0, 32, stream));
   const size_t tmp_bytes = tmp_a > tmp_b ? tmp_a : tmp_b;
   unsigned char* d_tmp;
-  BUILD_TRY(scratch.alloc(&d_tmp, tmp_bytes));
+  scratch.want(&d_pos, (size_t)n * 9);
+  scratch.want(&d_nrm, (size_t)n * 9);
+  scratch.want(&d_uv, (size_t)n * 6);
+  scratch.want(&d_bmin, (size_t)n * 3);
+  scratch.want(&d_bmax, (size_t)n * 3);
+  scratch.want(&d_cen, (size_t)n * 3);
+  scratch.want(&d_perm, n);
+  scratch.want(&d_perm2, n);
+  scratch.want(&d_place, n);
+  scratch.want(&d_place_sorted, n);
+  scratch.want(&d_place_sorted2, n);
+  scratch.want(&d_iota, n);
+  scratch.want(&d_vals, n);
+  scratch.want(&d_cen_key, n);
+  scratch.want(&d_cen_key2, n);
+  scratch.want(&d_seg_of_pos, n);
+  scratch.want(&d_segs, total_segs);
+  scratch.want(&d_bounds, max_segs * 6);
+  scratch.want(&d_seg_axis, max_segs);
+  scratch.want(&d_node_axes, n_nodes);
+  scratch.want(&d_topo, n_nodes);
+  scratch.want(&d_ids, n_nodes);
+  scratch.want(&d_tmp, tmp_bytes);
+  BUILD_TRY(scratch.commit());
 
   // the results outlive this call
   FlatNode* d_nodes = nullptr;

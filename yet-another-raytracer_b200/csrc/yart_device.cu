@@ -228,7 +228,7 @@ struct yart_ctx {
   uint32_t n_meshes = 0;
   uint32_t max_stack = 0;
   bool has_media = false;
-  uint32_t builder = YART_BUILDER_HOST;
+  uint32_t builder = YART_BUILDER_DEVICE;
   double* d_cie = nullptr;
   double* d_smits = nullptr;
 
