@@ -301,7 +301,10 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         # dominant kernel: k_trace.  algorithmic bytes of all its launches / their summed CUDA-event time
-        trace_launches = max(1, trace_launches)  # k_traverse x2 + k_analytic per bounce
+        trace_launches = max(1, trace_launches)
+        # closest-hit launches per bounce: one k_traverse per mesh instance (+ one k_analytic per run of analytic
+        # objects that k_shade does not take over); david: 2
+        passes = max(1, round(trace_launches / float(K * MAX_DEPTH)))
         achieved = bytes_per_ray * rays / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": N, "steps": K, "warmup": W,
@@ -324,11 +327,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "closest-hit stage (k_traverse x2 instances + k_analytic per bounce; k_traverse is ~93 % of it)", "achieved": achieved, "peak": peak,
+                "bound": "hbm", "kernel": "closest-hit stage: k_traverse, %d launches per bounce (one per mesh instance)" % passes, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": (profiled_traffic_per_ray() * rays / (trace_launches / 3.0)) if profiled_traffic_per_ray() else None,
+                "traffic": (profiled_traffic_per_ray() * rays / (trace_launches / float(passes))) if profiled_traffic_per_ray() else None,
                 "traffic_note": "bytes per k_traverse launch = 91.9 B/ray (dram read+write from the ncu --set full capture in "
-                                "profiles/r1_traffic.json) x this run's average rays per k_traverse launch (3 closest-hit launches per bounce); ~20x below the algorithmic bytes because "
+                                "profiles/r1_traffic.json) x this run's average rays per k_traverse launch; ~20x below the algorithmic bytes because "
                                 "node/triangle fetches hit L1/L2",
                 "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "trace_launches": int(trace_launches),
