@@ -35,7 +35,7 @@ if str(ROOT) not in sys.path:
 
 SCENE = "david"
 WIDTH, HEIGHT, MAX_DEPTH, TOTAL_SPP = 1920, 1080, 50, 1024
-SPP_PER_STEP = 32
+SPP_PER_STEP = 128  # one wavefront batch: 265 M paths in flight, 36 GB of path state (of 180 GB)
 SEED = 1
 METRIC = "Mrays/s (primary+secondary) on david.obj 1920x1080 max-depth 50"
 # bytes one ray moves besides node/triangle fetches: 48 B ray + 8 B time + 4 B queue entry read,
@@ -315,8 +315,8 @@ def run_ours(args):
                             "steps = the 1024-spp job)" % (SPP_PER_STEP, TOTAL_SPP // SPP_PER_STEP),
                 "scene": SCENE, "width": WIDTH, "height": HEIGHT, "max_depth": MAX_DEPTH, "spp_per_step": SPP_PER_STEP,
                 "spp_total": SPP_PER_STEP * K * N, "seed": SEED, "traversal_order": "near (bit-identical hits)",
-                "l2": "inputs larger than L2: 9 GB of path state streams per step; the 7 MB scene is meant to "
-                      "stay L2-resident",
+                "l2": "inputs larger than L2: %.0f GB of path state streams per step; the 7 MB scene is meant to "
+                      "stay L2-resident" % (WIDTH * HEIGHT * SPP_PER_STEP * 136 / 1e9),
                 "parallelism": "sample-range sharding x%d, scene replicated, one NCCL reduce of the f64 film" % N,
             },
             "spp_per_s": all_paths / (ms * 1e-3) / (WIDTH * HEIGHT),

@@ -121,7 +121,7 @@ def test_render_is_deterministic_and_sample_ranges_add_up(yart, orc, ctx):
 def test_full_size_frame_matches_oracle_and_batches_add_up(yart, orc, ctx):
     """BASELINE.json config 3 at its real frame (david, 1920x1080, depth 50), two samples per pixel against the
     oracle on every pixel; then the size-independent property at a sample count that spans two device batches
-    (32 spp per batch at this frame): film[0,34) == film[0,32) chained with [32,34), bit for bit."""
+    (batch_spp=32: a 32-spp and a 2-spp batch): film[0,34) == film[0,32) chained with [32,34), bit for bit."""
     preset = yart.ScenePreset("david")
     s = orc.Scene(preset)
     ctx.set_scene(preset)
@@ -132,7 +132,7 @@ def test_full_size_frame_matches_oracle_and_batches_add_up(yart, orc, ctx):
     compare_films(got, want, "david 1920x1080", 0.9995)
     assert st.paths == st_w.paths == w * h * 2
     assert abs(int(st.rays) - int(st_w.rays)) <= 64
-    whole, st34 = ctx.render(cam, w, h, 0, 34, max_depth=50, seed=3)
+    whole, st34 = ctx.render(cam, w, h, 0, 34, max_depth=50, seed=3, batch_spp=32)
     part, _ = ctx.render(cam, w, h, 0, 32, max_depth=50, seed=3)
     part, _ = ctx.render(cam, w, h, 32, 34, max_depth=50, seed=3, film=part)
     assert np.array_equal(whole, part)

@@ -894,9 +894,11 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
   uint32_t deepest = 0;
   if (n_samples > 0) {
     // batch shape: whole frame x spp_batch, or pixel chunks when the frame alone is too large
-    // Big batches: every batch pays ~12 ms of fixed cost (4 launches per bounce x 50 bounces, nearly empty
-    // tail bounces), so put up to 64 Mi paths in flight (136 B of state each = 9 GB of the 180 GB).
-    const uint64_t kMaxPaths = 1ull << 26;
+    // Big batches: every batch pays ~12 ms of fixed cost (the nearly empty tail bounces run at the latency of
+    // their longest ray), so put up to 256 Mi paths in flight (136 B of state each = 36.5 GB of the 180 GB):
+    // david 1080p at 32 / 64 / 128 spp per batch = 1121 / 1146 / 1158 Mrays/s.
+    static const int max_paths_log2 = std::max(10, std::min(30, tune_env("YART_TUNE_MAX_PATHS_LOG2", 28)));
+    const uint64_t kMaxPaths = 1ull << max_paths_log2;
     uint32_t spp_batch = o->batch_spp ? o->batch_spp : (uint32_t)std::max<uint64_t>(1, kMaxPaths / n_pixels_total);
     spp_batch = std::min(spp_batch, n_samples);
     uint32_t pix_chunk = n_pixels_total;
