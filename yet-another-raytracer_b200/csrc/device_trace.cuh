@@ -15,7 +15,10 @@
 
 namespace yart {
 
-constexpr int kTraceThreads = 128;
+#ifndef YART_TRACE_THREADS
+#define YART_TRACE_THREADS 128
+#endif
+constexpr int kTraceThreads = YART_TRACE_THREADS;
 constexpr uint32_t kSentinel = 0x7FFFFFFFu; // "no traversal in progress" (never a valid node id)
 
 
