@@ -143,6 +143,7 @@ struct DevGroup {
   const uint32_t* member_orig; // tree position -> index in yart_group.members
   uint32_t root;      // 0xFFFFFFFF when the group is tiny and scanned linearly
   uint32_t n_members;
+  double bound[3];    // max |coordinate| of the node boxes per axis (error bound of the f32 slab test)
 };
 
 struct DevImage {

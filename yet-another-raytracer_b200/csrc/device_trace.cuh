@@ -155,6 +155,20 @@ YART_DEV bool group_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
   int sp = 0;
   stack[sp++] = g.root;
   const double ix = 1.0 / rd.x, iy = 1.0 / rd.y, iz = 1.0 / rd.z;
+  // The boxes only cull, so the test may err on the side of visiting: a conservative f32 slab test (the
+  // error bound of k_traverse's MIXED path: |t32 - t64| <= 2^-22 |t32| + A) that skips a child only when it is
+  // PROVABLY missed needs no exact fallback.  Rays whose f32 image is unusable take the f64 test.
+  const float ixf = (float)ix, iyf = (float)iy, izf = (float)iz;
+  const float cxf = (float)(-(ro.x * ix)), cyf = (float)(-(ro.y * iy)), czf = (float)(-(ro.z * iz));
+  const double am = fmax(fmax((g.bound[0] + fabs(ro.x)) * fabs(ix), (g.bound[1] + fabs(ro.y)) * fabs(iy)),
+                         (g.bound[2] + fabs(ro.z)) * fabs(iz));
+  const float amax2 = __double2float_ru(am * (1.0 / 4194304.0));
+  const float lo_ok = 1e-30f, hi_ok = 1e30f;
+  const bool f32_ok = fabsf(ixf) > lo_ok && fabsf(ixf) < hi_ok && fabsf(iyf) > lo_ok && fabsf(iyf) < hi_ok &&
+                      fabsf(izf) > lo_ok && fabsf(izf) < hi_ok && fabsf(cxf) < hi_ok && fabsf(cyf) < hi_ok &&
+                      fabsf(czf) < hi_ok && amax2 < hi_ok && isfinite(ro.x) && isfinite(ro.y) && isfinite(ro.z);
+  const float t_min_f = (float)t_min;
+  const bool px = rd.x >= 0.0, py = rd.y >= 0.0, pz = rd.z >= 0.0;
   while (sp > 0) {
     const uint32_t id = stack[--sp];
     if (id >> 31) {
@@ -178,18 +192,31 @@ YART_DEV bool group_hit_t(const DevScene& S, const yart_object& o, D3 ro, D3 rd,
       const float lo[4][3] = {{mnx.x, mny.x, mnz.x}, {mnx.y, mny.y, mnz.y}, {mnx.z, mny.z, mnz.z}, {mnx.w, mny.w, mnz.w}};
       const float hi[4][3] = {{mxx.x, mxy.x, mxz.x}, {mxx.y, mxy.y, mxz.y}, {mxx.z, mxy.z, mxz.z}, {mxx.w, mxy.w, mxz.w}};
       const uint32_t cid[4] = {ch.x, ch.y, ch.z, ch.w};
+      const float closest_f = (float)closest;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (cid[k] == 0xFFFFFFFFu) continue;
-        // group boxes are padded outward by the builder, so a conservative >= test is safe
-        double t0 = ((double)lo[k][0] - ro.x) * ix, t1 = ((double)hi[k][0] - ro.x) * ix;
-        double tn = fmax(t_min, fmin(t0, t1)), tf = fmin(closest, fmax(t0, t1));
-        t0 = ((double)lo[k][1] - ro.y) * iy; t1 = ((double)hi[k][1] - ro.y) * iy;
-        tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
-        t0 = ((double)lo[k][2] - ro.z) * iz; t1 = ((double)hi[k][2] - ro.z) * iz;
-        tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
-        YART_CHECK(sp < 24 || !(tf >= tn));
-        if (tf >= tn && sp < 24) stack[sp++] = cid[k];
+        bool visit;
+        if (f32_ok) {
+          const float tn = fmaxf(fmaxf(t_min_f, fmaf(px ? lo[k][0] : hi[k][0], ixf, cxf)),
+                                 fmaxf(fmaf(py ? lo[k][1] : hi[k][1], iyf, cyf), fmaf(pz ? lo[k][2] : hi[k][2], izf, czf)));
+          const float tf = fminf(fminf(closest_f, fmaf(px ? hi[k][0] : lo[k][0], ixf, cxf)),
+                                 fminf(fmaf(py ? hi[k][1] : lo[k][1], iyf, cyf), fmaf(pz ? hi[k][2] : lo[k][2], izf, czf)));
+          const float gap = tf - tn;
+          const float e = fmaf(fabsf(tf) + fabsf(tn), 2.384185791015625e-7f, amax2);
+          visit = !(gap < -e); // not provably missed (NaN compares false: visit)
+        } else {
+          // group boxes are padded outward by the builder, so a conservative >= test is safe
+          double t0 = ((double)lo[k][0] - ro.x) * ix, t1 = ((double)hi[k][0] - ro.x) * ix;
+          double tn = fmax(t_min, fmin(t0, t1)), tf = fmin(closest, fmax(t0, t1));
+          t0 = ((double)lo[k][1] - ro.y) * iy; t1 = ((double)hi[k][1] - ro.y) * iy;
+          tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
+          t0 = ((double)lo[k][2] - ro.z) * iz; t1 = ((double)hi[k][2] - ro.z) * iz;
+          tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
+          visit = tf >= tn;
+        }
+        YART_CHECK(sp < 24 || !visit);
+        if (visit && sp < 24) stack[sp++] = cid[k];
       }
     }
   }

@@ -663,6 +663,11 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
         ctx->free_scene();
         return YART_ERR_INVALID;
       }
+    if (g.n_members > 65536u) { // tree height <= 7 keeps the traversal within its 24-entry stack (3 * height + 1)
+      ctx->err = "yart_ctx_set_scene: a group holds more than 65536 members";
+      ctx->free_scene();
+      return YART_ERR_UNSUPPORTED;
+    }
     std::vector<yart_object> members(g.members, g.members + g.n_members);
     std::vector<uint32_t> orig(g.n_members);
     std::iota(orig.begin(), orig.end(), 0u);
@@ -691,6 +696,14 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
     groups[i].member_orig = dorig;
     groups[i].root = root;
     groups[i].n_members = g.n_members;
+    for (int a = 0; a < 3; ++a) groups[i].bound[a] = 0.0;
+    for (const FlatNode& nd : gb.nodes)
+      for (int k = 0; k < 4; ++k) {
+        if (nd.child[k] == 0xFFFFFFFFu) continue;
+        groups[i].bound[0] = std::fmax(groups[i].bound[0], std::fmax(std::fabs((double)nd.min_x[k]), std::fabs((double)nd.max_x[k])));
+        groups[i].bound[1] = std::fmax(groups[i].bound[1], std::fmax(std::fabs((double)nd.min_y[k]), std::fabs((double)nd.max_y[k])));
+        groups[i].bound[2] = std::fmax(groups[i].bound[2], std::fmax(std::fabs((double)nd.min_z[k]), std::fabs((double)nd.max_z[k])));
+      }
   }
   // ---- images ----
   std::vector<DevImage> images(d->n_images);
