@@ -300,6 +300,10 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        # the fetch rooflines of SURVEY.md 8(d), measured live (untimed, ~50 ms): random whole-line (128 B = one
+        # node visit) fetches from an L1-resident table and from a table the size of the scene (L2-resident)
+        l1_fetch = max(ctx.measure_fetch_peak(128 * 1024, 4096, 0) for _ in range(3))
+        l2_fetch = max(ctx.measure_fetch_peak(7_400_000, 4096, 0) for _ in range(3))
         # dominant kernel: k_trace.  algorithmic bytes of all its launches / their summed CUDA-event time
         trace_launches = max(1, trace_launches)
         # closest-hit launches per bounce: one k_traverse per mesh instance (+ one k_analytic per run of analytic
@@ -333,6 +337,12 @@ def run_ours(args):
                 "traffic_note": "bytes per k_traverse launch = 91.9 B/ray (dram read+write from the ncu --set full capture in "
                                 "profiles/r1_traffic.json) x this run's average rays per k_traverse launch; ~20x below the algorithmic bytes because "
                                 "node/triangle fetches hit L1/L2",
+                "fetch_peaks": {"l1_resident_gbs": l1_fetch, "scene_sized_l2_resident_gbs": l2_fetch,
+                                "frac_of_l1_resident": (achieved / l1_fetch) if achieved else None,
+                                "frac_of_l2_resident": (achieved / l2_fetch) if achieved else None,
+                                "note": "yart_measure_fetch_peak: every lane fetches whole 128-B lines (four "
+                                        "LDG.E.256) at independent random positions, 16 warps per SM like k_traverse; "
+                                        "the closest-hit stage's fetches are ~70 % L1 hits, the rest L2 hits"},
                 "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "trace_launches": int(trace_launches),
                 "avg_launch_ms": trace_ms / trace_launches, "trace_share_of_step": trace_ms / ms if ms else None,

@@ -205,3 +205,14 @@ def test_all_f64_slab_path_gives_the_same_hits(yart, orc, mesh_scene, tmp_path):
     subprocess.run([sys.executable, "-c", code], check=True, env=env)
     for order in (0, 1):
         assert_same_hits(np.load(tmp_path / ("hits%d.npy" % order)), want, "f64 path order %d" % order)
+
+
+def test_fetch_peak_diagnostic(yart, ctx):
+    """yart_measure_fetch_peak (the L1 / L2 fetch roofline of SURVEY.md 8(d)): sane numbers, loud argument errors."""
+    l1 = ctx.measure_fetch_peak(128 * 1024, 1024, 0)
+    l2 = ctx.measure_fetch_peak(7_400_000, 1024, 0)
+    assert 1000.0 < l2 < 40000.0 and 1000.0 < l1 < 40000.0 and l1 > 0.9 * l2
+    with pytest.raises(yart.YartError):
+        ctx.measure_fetch_peak(64, 1024, 0)
+    with pytest.raises(yart.YartError):
+        ctx.measure_fetch_peak(1 << 20, 0, 0)

@@ -66,6 +66,7 @@ def load_library():
         "yart_qbvh_shade": (vp, [vp]),
         "yart_qbvh_build_device": (i32, [vp, P(abi.Trimesh), P(vp)]),
         "yart_ctx_set_builder": (i32, [vp, u32]),
+        "yart_measure_fetch_peak": (i32, [vp, u64, u32, u32, P(f64)]),
         "yart_preset_build": (i32, [C.c_char_p, C.c_char_p, u64, P(vp)]),
         "yart_preset_free": (None, [vp]),
         "yart_preset_scene": (P(abi.SceneDesc), [vp]),
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "yart_resolve_dimensions", "yart_preset_camera", "yart_device_count", "yart_ctx_create", "yart_ctx_destroy",
     "yart_last_error", "yart_ctx_set_stream", "yart_ctx_synchronize", "yart_ctx_set_scene", "yart_closest_hit",
     "yart_render", "yart_film_finalize", "yart_generate_camera_rays", "yart_qbvh_shade", "yart_qbvh_build_device",
-    "yart_ctx_set_builder",
+    "yart_ctx_set_builder", "yart_measure_fetch_peak",
 ]
 
 
@@ -288,6 +289,12 @@ class Context:
     def set_builder(self, builder):
         """BUILDER_DEVICE (default) or BUILDER_HOST: which L4QBVH builder set_scene uses for meshes."""
         self._check(_lib.yart_ctx_set_builder(self._h, builder))
+
+    def measure_fetch_peak(self, table_bytes, fetches_per_thread=2048, mode=0):
+        """Sustained GB/s of random whole-line (128 B) fetches from a table of this size (roofline denominator)."""
+        out = C.c_double()
+        self._check(_lib.yart_measure_fetch_peak(self._h, int(table_bytes), int(fetches_per_thread), int(mode), C.byref(out)))
+        return float(out.value)
 
     def set_stream(self, cuda_stream_ptr):
         self._check(_lib.yart_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))

@@ -57,6 +57,23 @@ __global__ void __launch_bounds__(256) k_export(const DevScene S, const yart_ray
   }
 }
 
+// yart_measure_fetch_peak: independent random 128-byte line fetches (one QBVH node visit = four LDG.E.256)
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_fetch_peak(const float4* __restrict__ table, uint32_t n_lines, uint32_t iters,
+                                                                     float* sink) {
+  uint32_t s = (blockIdx.x * THREADS + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0.f;
+#pragma unroll 4
+  for (uint32_t i = 0; i < iters; ++i) {
+    s = s * 1664525u + 1013904223u;
+    const uint32_t line = (uint32_t)(((uint64_t)s * n_lines) >> 32);
+    const float4* p = table + (size_t)line * 8;
+    const F8 a = ldg256(p), b = ldg256(p + 2), c = ldg256(p + 4), d = ldg256(p + 6);
+    acc += a.lo.x + b.hi.y + c.lo.z + d.hi.w;
+  }
+  if (acc == 1234.5678f) sink[0] = acc; // keeps the loads alive
+}
+
 namespace {
 
 #define CUDA_TRY(ctx, expr)                                                                  \
@@ -1103,6 +1120,51 @@ int yart_generate_camera_rays(yart_ctx* ctx, const yart_camera* cam, const yart_
     CUDA_TRY(ctx, cudaMemcpyAsync(wavelength_host, ctx->wavelength.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (time_host) CUDA_TRY(ctx, cudaMemcpyAsync(time_host, ctx->time.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return YART_OK;
+}
+
+int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetches_per_thread, uint32_t mode,
+                            double* gbytes_per_s) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!gbytes_per_s || table_bytes < 128 || table_bytes > (1ull << 36) || fetches_per_thread == 0 || mode > 1) {
+    ctx->err = "yart_measure_fetch_peak: bad argument";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const uint32_t n_lines = (uint32_t)std::min<uint64_t>(table_bytes / 128, 0x7FFFFFFFull);
+  DevBuf table, sink;
+  cudaError_t e = table.reserve((size_t)n_lines * 128);
+  if (e == cudaSuccess) e = sink.reserve(64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(table.p, 0, (size_t)n_lines * 128, ctx->stream);
+  float ms = 0.f;
+  size_t threads = 0;
+  if (e == cudaSuccess) {
+    static const int carve = tune_env("YART_TUNE_CARVEOUT", 35);
+    auto run = [&](auto kernel, int block, bool set_carve) {
+      if (set_carve) cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      int per_sm = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(kernel), block, 0);
+      const int grid = std::max(per_sm, 1) * ctx->sm_count;
+      threads = (size_t)grid * block;
+      kernel<<<grid, block, 0, ctx->stream>>>(table.as<float4>(), n_lines, fetches_per_thread / 8 + 1, sink.as<float>()); // warm L2
+      cudaEventRecord(ctx->ev0, ctx->stream);
+      kernel<<<grid, block, 0, ctx->stream>>>(table.as<float4>(), n_lines, fetches_per_thread, sink.as<float>());
+      cudaEventRecord(ctx->ev1, ctx->stream);
+    };
+    // mode 0: 128-thread CTAs, 4 per SM -- 16 warps per SM like k_traverse (its register budget, not this
+    // kernel's, is what limits it), same carveout; mode 1: whatever fits
+    if (mode == 0) run(k_fetch_peak<128, 4>, 128, true);
+    else run(k_fetch_peak<256, 8>, 256, false);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  }
+  table.release();
+  sink.release();
+  if (e != cudaSuccess) {
+    ctx->err = std::string("yart_measure_fetch_peak: ") + cudaGetErrorString(e);
+    return YART_ERR_CUDA;
+  }
+  *gbytes_per_s = (double)threads * fetches_per_thread * 128.0 / (ms * 1e-3) / 1e9;
   return YART_OK;
 }
 
