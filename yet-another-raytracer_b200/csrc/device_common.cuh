@@ -106,6 +106,8 @@ YART_DEV F8 ldg256(const float4* p) {
   return r;
 }
 
+YART_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---------------------------------------------------------------------------------------------
 // Scene in HBM
 // ---------------------------------------------------------------------------------------------

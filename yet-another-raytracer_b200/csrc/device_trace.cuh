@@ -282,7 +282,7 @@ struct TraverseParams {
   uint32_t wrap;              // YART_WRAP_ROTATE_Y / TRANSLATE of this instance
   uint32_t refill_threshold;  // run the retire/fetch phase once this many lanes wait for it
   uint32_t node_threshold;    // leave the inner-node loop once fewer lanes than this are in it
-  uint32_t _pad;
+  uint32_t lookahead;         // fetch phase: prefetch the ray / hit of the work item this far ahead into L2 (0 = off)
   uint32_t n_nodes, n_tris;   // array lengths (bounds-checked build)
   double sin_theta, cos_theta, offset[3];
   double bound[3];            // max |coordinate| of the mesh per axis (for the f32 slab error bound)
@@ -428,6 +428,13 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
         } else {
           ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
           YART_CHECK(ray_id < P.c.n_rays);
+          // The ray and hit records of a work item are DRAM misses on the warp's critical path (the whole warp
+          // waits in this phase).  Items are handed out in order, so the records of item + lookahead will be
+          // wanted by some lane a few microseconds from now: pull them into L2 (the id load is issued here and
+          // consumed after this lane's own setup, so it costs no wait).
+          const uint64_t ahead = item + P.lookahead;
+          uint32_t ahead_id = YART_MISS;
+          if (P.lookahead && ahead < n_items) ahead_id = P.c.queue ? P.c.queue[ahead] : (uint32_t)ahead;
           const yart_ray wr = P.c.rays[ray_id];
           t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
           D3 ro = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
@@ -471,6 +478,13 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           t_entry = t_best;
           best_prim = YART_MISS;
           best_bu = best_bv = 0.0;
+          if (ahead_id != YART_MISS) {
+            YART_CHECK(ahead_id < P.c.n_rays);
+            const char* rp = reinterpret_cast<const char*>(P.c.rays + ahead_id);
+            prefetch_l2(rp);
+            prefetch_l2(rp + 32); // a 48-byte record always spans two 32-byte sectors
+            if (!P.c.first_pass) prefetch_l2(P.c.hits + ahead_id);
+          }
         }
       }
     }
