@@ -282,7 +282,7 @@ struct TraverseParams {
   uint32_t wrap;              // YART_WRAP_ROTATE_Y / TRANSLATE of this instance
   uint32_t refill_threshold;  // run the retire/fetch phase once this many lanes wait for it
   uint32_t node_threshold;    // leave the inner-node loop once fewer lanes than this are in it
-  uint32_t lookahead;         // fetch phase: prefetch the ray / hit of the work item this far ahead into L2 (0 = off)
+  uint32_t _pad;
   uint32_t n_nodes, n_tris;   // array lengths (bounds-checked build)
   double sin_theta, cos_theta, offset[3];
   double bound[3];            // max |coordinate| of the mesh per axis (for the f32 slab error bound)
@@ -367,7 +367,23 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
   const uint32_t rpw = (uint32_t)max((unsigned long long)1, min((unsigned long long)32, (unsigned long long)((n_items + total_warps - 1) / total_warps)));
   const uint64_t dyn_base = total_warps * rpw;
   if ((uint64_t)warp_global * rpw >= n_items) return;
-  bool first_fetch = true;
+  // Work items reach the lanes through a two-deep pipeline of 32-item chunks, so that neither the claim
+  // (an atomic), nor the queue read, nor the DRAM miss of the ray record sits on the warp's critical path:
+  //   chunk "cur": ids held one per lane (id_cur), handed to fetching lanes by shuffle;
+  //   chunk "nxt": claimed when cur was started (stage 1: atomic in flight), ids loaded one retire/fetch phase
+  //   later (stage 2), ray / hit records prefetched into L2 the phase after (stage 3).
+  // The first chunk of a warp is its static slice; all later ones come from the global counter.
+  uint64_t cur_base = (uint64_t)warp_global * rpw;
+  uint32_t cur_cnt = (uint32_t)min((unsigned long long)rpw, (unsigned long long)(n_items - cur_base));
+  uint32_t cur_used = 0;
+  uint32_t id_cur = YART_MISS, id_nxt = YART_MISS, claim_raw = 0;
+  if (lane < cur_cnt) id_cur = P.c.queue ? P.c.queue[cur_base + lane] : (uint32_t)(cur_base + lane);
+  bool dyn_done = dyn_base >= n_items; // nothing beyond the static slices: never touch the counter
+  uint32_t nxt_cnt = 0, nxt_stage = 0;
+  if (!dyn_done) {
+    if (lane == 0) claim_raw = atomicAdd(P.work_counter, 32u);
+    nxt_stage = 1;
+  }
   const uint32_t RT = P.refill_threshold, NT = P.node_threshold;
   const float4* __restrict__ nodes = P.nodes;
   const float4* __restrict__ tris = P.tris;
@@ -394,8 +410,8 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
     const bool want_a = (cur == kSentinel) && !(exhausted && ray_id == YART_MISS);
     const uint32_t a_mask = __ballot_sync(0xffffffffu, want_a);
     const uint32_t busy_mask = __ballot_sync(0xffffffffu, cur != kSentinel);
-    if (want_a && ((uint32_t)__popc(a_mask) >= RT || busy_mask == 0)) {
-      if (ray_id != YART_MISS) { // retire: record the hit if this mesh improved on the earlier objects
+    if (a_mask != 0 && ((uint32_t)__popc(a_mask) >= RT || busy_mask == 0)) { // (warp-uniform)
+      if (want_a && ray_id != YART_MISS) { // retire: record the hit if this mesh improved on the earlier objects
         if (best_prim != YART_MISS) {
           DevHit h;
           h.t = t_best; h.bu = best_bu; h.bv = best_bv; h.obj = P.obj_index; h.prim = best_prim;
@@ -407,34 +423,69 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
         }
         ray_id = YART_MISS;
       }
-      const uint32_t fmask = __ballot_sync(a_mask, !exhausted);
-      if (!exhausted) { // fetch: one atomic for all fetching lanes of the warp
-        uint64_t item;
-        if (first_fetch) { // (all 32 lanes of the warp are here together the first time)
-          item = (lane < rpw) ? (uint64_t)warp_global * rpw + lane : n_items;
-          first_fetch = false;
-        } else if (dyn_base >= n_items) {
-          item = n_items; // nothing beyond the static slices: no need to touch the counter
-        } else {
-          const int leader = __ffs(fmask) - 1;
-          const uint32_t rank = __popc(fmask & ((1u << lane) - 1u));
-          uint32_t base = 0;
-          if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(fmask));
-          base = __shfl_sync(fmask, base, leader);
-          item = dyn_base + base + rank;
+      // ---- advance the chunk pipeline by one stage (warp-uniform) ----
+      if (nxt_stage == 2) {
+        if (id_nxt != YART_MISS) {
+          YART_CHECK(id_nxt < P.c.n_rays);
+          const char* rp = reinterpret_cast<const char*>(P.c.rays + id_nxt);
+          prefetch_l2(rp);
+          prefetch_l2(rp + 32); // a 48-byte record always spans two 32-byte sectors
+          if (!P.c.first_pass) prefetch_l2(P.c.hits + id_nxt);
         }
-        if (item >= n_items) {
-          exhausted = true;
+        nxt_stage = 3;
+      }
+      // ---- hand out items (all lanes take part in the shuffles) ----
+      const bool fetching = want_a && !exhausted;
+      const uint32_t fmask = __ballot_sync(0xffffffffu, fetching);
+      const uint32_t need = (uint32_t)__popc(fmask);
+      const uint32_t rank = (uint32_t)__popc(fmask & ((1u << lane) - 1u));
+      const uint32_t take1 = min(need, cur_cnt - cur_used);
+      uint32_t new_id = __shfl_sync(0xffffffffu, id_cur, (cur_used + rank) & 31u);
+      bool got = fetching && rank < take1;
+      cur_used += take1;
+      if (need > take1) { // the current chunk ran out: the next one becomes current, and another is claimed
+        if (nxt_stage == 1) { // its claim has come back by now: read its ids
+          const uint64_t nb = dyn_base + __shfl_sync(0xffffffffu, claim_raw, 0);
+          nxt_cnt = nb < n_items ? (uint32_t)min((unsigned long long)32, (unsigned long long)(n_items - nb)) : 0u;
+          id_nxt = YART_MISS;
+          if (lane < nxt_cnt) id_nxt = P.c.queue ? P.c.queue[nb + lane] : (uint32_t)(nb + lane);
+          if (nxt_cnt < 32u) dyn_done = true; // the counter has passed the end of the queue
+          nxt_stage = 2;
+        }
+        if (nxt_stage >= 2) {
+          id_cur = id_nxt;
+          cur_cnt = nxt_cnt;
         } else {
-          ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
+          cur_cnt = 0;
+        }
+        cur_used = 0;
+        nxt_stage = 0;
+        nxt_cnt = 0;
+        if (!dyn_done) {
+          if (lane == 0) claim_raw = atomicAdd(P.work_counter, 32u);
+          nxt_stage = 1;
+        }
+        const uint32_t rank2 = rank - take1; // (meaningful for the lanes that are still waiting)
+        const uint32_t take2 = min(need - take1, cur_cnt);
+        const uint32_t id2 = __shfl_sync(0xffffffffu, id_cur, rank2 & 31u);
+        if (fetching && !got && rank2 < take2) {
+          new_id = id2;
+          got = true;
+        }
+        cur_used = take2;
+        if (fetching && !got) exhausted = true; // only possible once the queue is used up
+      } else if (nxt_stage == 1) { // no swap this time: use the phase to resolve the claim and load the ids
+        const uint64_t nb = dyn_base + __shfl_sync(0xffffffffu, claim_raw, 0);
+        nxt_cnt = nb < n_items ? (uint32_t)min((unsigned long long)32, (unsigned long long)(n_items - nb)) : 0u;
+        id_nxt = YART_MISS;
+        if (lane < nxt_cnt) id_nxt = P.c.queue ? P.c.queue[nb + lane] : (uint32_t)(nb + lane);
+        if (nxt_cnt < 32u) dyn_done = true;
+        nxt_stage = 2;
+      }
+      if (got) {
+        {
+          ray_id = new_id;
           YART_CHECK(ray_id < P.c.n_rays);
-          // The ray and hit records of a work item are DRAM misses on the warp's critical path (the whole warp
-          // waits in this phase).  Items are handed out in order, so the records of item + lookahead will be
-          // wanted by some lane a few microseconds from now: pull them into L2 (the id load is issued here and
-          // consumed after this lane's own setup, so it costs no wait).
-          const uint64_t ahead = item + P.lookahead;
-          uint32_t ahead_id = YART_MISS;
-          if (P.lookahead && ahead < n_items) ahead_id = P.c.queue ? P.c.queue[ahead] : (uint32_t)ahead;
           const yart_ray wr = P.c.rays[ray_id];
           t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
           D3 ro = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
@@ -478,13 +529,6 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           t_entry = t_best;
           best_prim = YART_MISS;
           best_bu = best_bv = 0.0;
-          if (ahead_id != YART_MISS) {
-            YART_CHECK(ahead_id < P.c.n_rays);
-            const char* rp = reinterpret_cast<const char*>(P.c.rays + ahead_id);
-            prefetch_l2(rp);
-            prefetch_l2(rp + 32); // a 48-byte record always spans two 32-byte sectors
-            if (!P.c.first_pass) prefetch_l2(P.c.hits + ahead_id);
-          }
         }
       }
     }

@@ -350,7 +350,6 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
   static const int rt = tune_env("YART_TUNE_RT", 8), nt = tune_env("YART_TUNE_NT", 12);
   static const int carve = tune_env("YART_TUNE_CARVEOUT", 35);
   static const int mixed = tune_env("YART_TUNE_MIXED", 1); // 0: all-f64 slab tests (same results, slower)
-  static const int lookahead = tune_env("YART_TUNE_LOOKAHEAD", 32768);
   bool first = true;
   uint32_t i = 0, n_trav = 0;
   auto is_mesh = [&](uint32_t k) {
@@ -387,7 +386,6 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       T.wrap = o.wrap & (YART_WRAP_ROTATE_Y | YART_WRAP_TRANSLATE);
       T.refill_threshold = (uint32_t)std::max(1, std::min(32, rt));
       T.node_threshold = (uint32_t)std::max(1, std::min(32, nt));
-      T.lookahead = (uint32_t)std::max(0, lookahead);
       T.sin_theta = o.sin_theta;
       T.cos_theta = o.cos_theta;
       for (int k = 0; k < 3; ++k) T.offset[k] = o.offset[k];
