@@ -651,10 +651,20 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
       const uint32_t first = cur & 0x7FFFFFFu;
       if (COUNT) n_tris += count;
       YART_CHECK(count >= 1 && count <= 4 && first + count <= P.n_tris);
+      // the next triangle's record is requested before the current one is tested (its ~100 dependent f64
+      // instructions then cover the fetch)
+      float4 n0, n1, n2;
+      {
+        const float4* tp = tris + (size_t)(first + (NEAR ? (count - 1u) : 0u)) * 3;
+        n0 = __ldg(tp); n1 = __ldg(tp + 1); n2 = __ldg(tp + 2);
+      }
       for (uint32_t j = 0; j < count; ++j) {
         const uint32_t i = NEAR ? (count - 1u - j) : j;
-        const float4* tp = tris + (size_t)(first + i) * 3;
-        const float4 a0 = __ldg(tp), a1 = __ldg(tp + 1), a2 = __ldg(tp + 2);
+        const float4 a0 = n0, a1 = n1, a2 = n2;
+        if (j + 1u < count) {
+          const float4* tp = tris + (size_t)(first + (NEAR ? (i - 1u) : (i + 1u))) * 3;
+          n0 = __ldg(tp); n1 = __ldg(tp + 1); n2 = __ldg(tp + 2);
+        }
         const double v0x = (double)a0.x, v0y = (double)a0.y, v0z = (double)a0.z;
         const double e1x = (double)a1.x - v0x, e1y = (double)a1.y - v0y, e1z = (double)a1.z - v0z;
         const double e2x = (double)a2.x - v0x, e2y = (double)a2.y - v0y, e2z = (double)a2.z - v0z;
