@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep per CUDA source line: instructions executed, average active threads,
-stall samples.  Usage: python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top_n]"""
+stall samples.  Usage: python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top_n] [--kernel NAME_SUBSTRING]
+(the first captured launch whose kernel name contains the substring; default: the first launch)"""
 import csv
 import subprocess
 import sys
@@ -9,8 +10,11 @@ from collections import defaultdict
 
 def main():
     rep = sys.argv[1]
-    top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"],
+    top = int(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else 40
+    extra = []
+    if "--kernel" in sys.argv:
+        extra = ["--kernel-name", "regex:" + sys.argv[sys.argv.index("--kernel") + 1], "--launch-count", "1"]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"] + extra,
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     agg = defaultdict(lambda: [0, 0, 0, ""])  # inst, thread inst, samples, text

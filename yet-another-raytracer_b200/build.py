@@ -39,7 +39,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "--shared", "-cudart", "shared",
 ]
-for knob in ("YART_TRAVERSE_MIN_BLOCKS", "YART_SHADE_MIN_BLOCKS", "YART_TRACE_THREADS"):  # tuning: resident blocks per SM compiled for
+for knob in ("YART_TRAVERSE_MIN_BLOCKS", "YART_SHADE_MIN_BLOCKS", "YART_TRACE_THREADS", "YART_SHADE_THREADS"):  # tuning: resident blocks per SM compiled for
     if os.environ.get(knob):
         NVCC_FLAGS += ["-D%s=%s" % (knob, os.environ[knob])]
 

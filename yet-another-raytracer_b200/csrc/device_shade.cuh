@@ -546,10 +546,14 @@ __global__ void __launch_bounds__(256) k_camera_rays(const RenderParams R, yart_
 // One bounce of ray_reflectance (main.rs:537-588) for every queued path.  Surviving paths are
 // appended to the next queue (warp-aggregated atomics = stream compaction); finished paths write
 // their sample value.  `bounce` is 1-based: the bounce-th world.hit of the path.
-#ifndef YART_SHADE_MIN_BLOCKS
-#define YART_SHADE_MIN_BLOCKS 4
+#ifndef YART_SHADE_THREADS
+#define YART_SHADE_THREADS 256
 #endif
-__global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const RenderParams R, const uint32_t* queue, const uint32_t* queue_count,
+#ifndef YART_SHADE_MIN_BLOCKS
+#define YART_SHADE_MIN_BLOCKS (1024 / YART_SHADE_THREADS)
+#endif
+constexpr int kShadeThreads = YART_SHADE_THREADS;
+__global__ void __launch_bounds__(kShadeThreads, YART_SHADE_MIN_BLOCKS) k_shade(const RenderParams R, const uint32_t* queue, const uint32_t* queue_count,
                                                 uint32_t* next_queue, uint32_t* next_count, uint32_t bounce) {
   const DevScene& S = R.scene;
   const uint32_t n = *queue_count;
@@ -557,8 +561,8 @@ __global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const Rend
   // Paths of one block are regrouped by what their hit needs (miss / emitter, Lambertian, dielectric,
   // other) before shading, so the warps run mostly one branch of the material switch.  Which thread
   // shades which path does not matter: every result is addressed by the path id.
-  __shared__ uint32_t s_ids[256];
-  __shared__ uint32_t s_cnt[8][4];
+  __shared__ uint32_t s_ids[kShadeThreads];
+  __shared__ uint32_t s_cnt[kShadeThreads / 32][4];
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     {
       const uint32_t it = base + threadIdx.x;
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(256, YART_SHADE_MIN_BLOCKS) k_shade(const Rend
       if (cls < 4) {
         uint32_t off = 0;
         for (uint32_t c = 0; c < cls; ++c)
-          for (uint32_t w = 0; w < 8; ++w) off += s_cnt[w][c];
+          for (uint32_t w = 0; w < kShadeThreads / 32; ++w) off += s_cnt[w][c];
         for (uint32_t w = 0; w < warp; ++w) off += s_cnt[w][cls];
         s_ids[off + rank] = my_id;
       }

@@ -1009,7 +1009,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
           rc = run_passes(ctx, q, &trace_launches);
           if (rc) return rc;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1) + 1], ctx->stream));
-          k_shade<<<stream_grid, 256, 0, ctx->stream>>>(R, qa, counts + b, qb, counts + b + 1, b);
+          k_shade<<<std::max(1, stream_grid * 256 / kShadeThreads), kShadeThreads, 0, ctx->stream>>>(R, qa, counts + b, qb, counts + b + 1, b);
           launches += 1;
           std::swap(qa, qb);
           b_done = b;
