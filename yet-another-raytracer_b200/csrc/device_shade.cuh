@@ -546,6 +546,126 @@ __global__ void __launch_bounds__(256) k_camera_rays(const RenderParams R, yart_
 // One bounce of ray_reflectance (main.rs:537-588) for every queued path.  Surviving paths are
 // appended to the next queue (warp-aggregated atomics = stream compaction); finished paths write
 // their sample value.  `bounce` is 1-based: the bounce-th world.hit of the path.
+// One bounce of one path: everything k_shade does for path `id` except the compaction of the survivors.
+// Returns true when the path goes on (its next ray and throughput are stored), false when it ended (its sample
+// value is stored).
+YART_DEV bool shade_path(const RenderParams& R, uint32_t id, uint32_t bounce) {
+  const DevScene& S = R.scene;
+  bool alive = false;
+  const uint32_t pixel = R.pixel_base + id / R.spp_batch;
+  const uint32_t sample = R.sample_base + id % R.spp_batch;
+  const Rng rng = make_rng(R.seed, pixel, sample);
+  const yart_ray wr = R.st.rays[id];
+  const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
+  const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+  const double time = R.st.time[id];
+  const double wl = R.st.wavelength[id];
+  double thr = R.st.throughput[id];
+  const DevHit h = R.st.hits[id];
+  double terminal = 0.0;
+  bool done = true;
+  D3 next_d = d3(0, 0, 0), next_o = d3(0, 0, 0);
+  if (h.obj == YART_MISS) {
+    terminal = rgb_reflect(S, S.background, wl); // main.rs:587
+  } else {
+    HitRec rec;
+    world_record(S, h, wo, wd, time, rec);
+    const yart_material& mat = S.materials[rec.material];
+    double emitted = 0.0;
+    if (mat.kind == YART_MAT_DIFFUSE_LIGHT) emitted = rec.front_face ? texture_value(S, mat.texture, wl, rec) : 0.0;
+    if (mat.kind == YART_MAT_NONE || mat.kind == YART_MAT_DIFFUSE_LIGHT) {
+      terminal = emitted;
+    } else if (mat.kind == YART_MAT_METAL) {
+      D3 reflected = reflect(unit_vector(wd), rec.normal);
+      next_d = reflected + mat.fuzz * random_in_unit_sphere(rng, bounce);
+      next_o = rec.p;
+      thr = thr * texture_value(S, mat.texture, wl, rec);
+      done = false;
+    } else if (mat.kind == YART_MAT_ISOTROPIC) {
+      next_d = random_in_unit_sphere(rng, bounce);
+      next_o = rec.p;
+      thr = thr * texture_value(S, mat.texture, wl, rec);
+      done = false;
+    } else if (mat.kind == YART_MAT_DIELECTRIC) { // material.rs:213-301
+      const double nidx = sellmeier_index(mat, wl);
+      D3 outward;
+      double ni_over_nt, cosine;
+      const double ddn = dot(wd, rec.normal);
+      if (ddn > 0.0) {
+        outward = -rec.normal;
+        ni_over_nt = nidx;
+        cosine = nidx * dot(wd, rec.normal) / length(wd);
+      } else {
+        outward = rec.normal;
+        ni_over_nt = 1.0 / nidx;
+        cosine = -dot(wd, rec.normal) / length(wd);
+      }
+      D3 refracted;
+      if (refract(wd, outward, ni_over_nt, refracted)) {
+        double u0, u1;
+        rng_draw(rng, bounce, YART_SLOT_DIELECTRIC, u0, u1);
+        next_d = (u0 < schlick(cosine, nidx)) ? reflect(wd, rec.normal) : refracted;
+      } else {
+        next_d = reflect(wd, rec.normal);
+      }
+      next_o = rec.p;
+      thr = thr * 1.0;
+      done = false;
+    } else { // Lambertian through the mixture pdf (material.rs:44-61, main.rs:560-581)
+      const double atten = texture_value(S, mat.texture, wl, rec);
+      const Onb uvw = onb_from_w(rec.normal);
+      double u_mix, u_pick, r1, r2;
+      rng_draw(rng, bounce, YART_SLOT_MIX, u_mix, u_pick);
+      rng_draw(rng, bounce, YART_SLOT_DIR, r1, r2);
+      const bool have_lights = S.n_lights != 0;
+      D3 dir;
+      if (u_mix < 0.5 && have_lights) {
+        dir = lights_random(S, rec.p, u_pick, r1, r2);
+      } else { // random_cosine_direction (pdf.rs:15-25)
+        const double z = sqrt(1.0 - r2);
+        const double phi = 2.0 * kPi * r1;
+        const double x = cos(phi) * sqrt(r2);
+        const double y = sin(phi) * sqrt(r2);
+        dir = onb_local(uvw, d3(x, y, z));
+      }
+      const double cosv = dot(unit_vector(dir), uvw.w);
+      const double cos_pdf = cosv <= 0.0 ? 0.0 : cosv / kPi;
+      const double p0 = have_lights ? lights_pdf_value(S, rec.p, dir) : cos_pdf;
+      const double pdf_val = 0.5 * p0 + 0.5 * cos_pdf;
+      if (!isfinite(pdf_val) || pdf_val <= 0.0) {
+        terminal = emitted;
+      } else {
+        const double cs = dot(rec.normal, unit_vector(dir));
+        const double spdf = cs < 0.0 ? 0.0 : cs / kPi;
+        thr = thr * atten * spdf / pdf_val;
+        next_o = rec.p;
+        next_d = dir;
+        done = false;
+      }
+    }
+  }
+  if (!done && bounce >= R.max_depth) { // depth exhausted: ray_reflectance(depth 0) = 1.0
+    done = true;
+    terminal = 1.0;
+  }
+  if (done) {
+    const double refl = thr * terminal;
+    double cie[3];
+    xyz_from_wavelength(S, wl, cie);
+    R.st.contrib[(size_t)id * 3 + 0] = cie[0] * refl;
+    R.st.contrib[(size_t)id * 3 + 1] = cie[1] * refl;
+    R.st.contrib[(size_t)id * 3 + 2] = cie[2] * refl;
+  } else {
+    yart_ray nr;
+    nr.origin[0] = next_o.x; nr.origin[1] = next_o.y; nr.origin[2] = next_o.z;
+    nr.direction[0] = next_d.x; nr.direction[1] = next_d.y; nr.direction[2] = next_d.z;
+    R.st.rays[id] = nr;
+    R.st.throughput[id] = thr;
+    alive = true;
+  }
+  return alive;
+}
+
 #ifndef YART_SHADE_THREADS
 #define YART_SHADE_THREADS 256
 #endif
@@ -621,117 +741,7 @@ __global__ void __launch_bounds__(kShadeThreads, YART_SHADE_MIN_BLOCKS) k_shade(
     uint32_t id = 0;
     if (item < n) {
       id = s_ids[threadIdx.x];
-      const uint32_t pixel = R.pixel_base + id / R.spp_batch;
-      const uint32_t sample = R.sample_base + id % R.spp_batch;
-      const Rng rng = make_rng(R.seed, pixel, sample);
-      const yart_ray wr = R.st.rays[id];
-      const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
-      const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
-      const double time = R.st.time[id];
-      const double wl = R.st.wavelength[id];
-      double thr = R.st.throughput[id];
-      const DevHit h = R.st.hits[id];
-      double terminal = 0.0;
-      bool done = true;
-      D3 next_d = d3(0, 0, 0), next_o = d3(0, 0, 0);
-      if (h.obj == YART_MISS) {
-        terminal = rgb_reflect(S, S.background, wl); // main.rs:587
-      } else {
-        HitRec rec;
-        world_record(S, h, wo, wd, time, rec);
-        const yart_material& mat = S.materials[rec.material];
-        double emitted = 0.0;
-        if (mat.kind == YART_MAT_DIFFUSE_LIGHT) emitted = rec.front_face ? texture_value(S, mat.texture, wl, rec) : 0.0;
-        if (mat.kind == YART_MAT_NONE || mat.kind == YART_MAT_DIFFUSE_LIGHT) {
-          terminal = emitted;
-        } else if (mat.kind == YART_MAT_METAL) {
-          D3 reflected = reflect(unit_vector(wd), rec.normal);
-          next_d = reflected + mat.fuzz * random_in_unit_sphere(rng, bounce);
-          next_o = rec.p;
-          thr = thr * texture_value(S, mat.texture, wl, rec);
-          done = false;
-        } else if (mat.kind == YART_MAT_ISOTROPIC) {
-          next_d = random_in_unit_sphere(rng, bounce);
-          next_o = rec.p;
-          thr = thr * texture_value(S, mat.texture, wl, rec);
-          done = false;
-        } else if (mat.kind == YART_MAT_DIELECTRIC) { // material.rs:213-301
-          const double nidx = sellmeier_index(mat, wl);
-          D3 outward;
-          double ni_over_nt, cosine;
-          const double ddn = dot(wd, rec.normal);
-          if (ddn > 0.0) {
-            outward = -rec.normal;
-            ni_over_nt = nidx;
-            cosine = nidx * dot(wd, rec.normal) / length(wd);
-          } else {
-            outward = rec.normal;
-            ni_over_nt = 1.0 / nidx;
-            cosine = -dot(wd, rec.normal) / length(wd);
-          }
-          D3 refracted;
-          if (refract(wd, outward, ni_over_nt, refracted)) {
-            double u0, u1;
-            rng_draw(rng, bounce, YART_SLOT_DIELECTRIC, u0, u1);
-            next_d = (u0 < schlick(cosine, nidx)) ? reflect(wd, rec.normal) : refracted;
-          } else {
-            next_d = reflect(wd, rec.normal);
-          }
-          next_o = rec.p;
-          thr = thr * 1.0;
-          done = false;
-        } else { // Lambertian through the mixture pdf (material.rs:44-61, main.rs:560-581)
-          const double atten = texture_value(S, mat.texture, wl, rec);
-          const Onb uvw = onb_from_w(rec.normal);
-          double u_mix, u_pick, r1, r2;
-          rng_draw(rng, bounce, YART_SLOT_MIX, u_mix, u_pick);
-          rng_draw(rng, bounce, YART_SLOT_DIR, r1, r2);
-          const bool have_lights = S.n_lights != 0;
-          D3 dir;
-          if (u_mix < 0.5 && have_lights) {
-            dir = lights_random(S, rec.p, u_pick, r1, r2);
-          } else { // random_cosine_direction (pdf.rs:15-25)
-            const double z = sqrt(1.0 - r2);
-            const double phi = 2.0 * kPi * r1;
-            const double x = cos(phi) * sqrt(r2);
-            const double y = sin(phi) * sqrt(r2);
-            dir = onb_local(uvw, d3(x, y, z));
-          }
-          const double cosv = dot(unit_vector(dir), uvw.w);
-          const double cos_pdf = cosv <= 0.0 ? 0.0 : cosv / kPi;
-          const double p0 = have_lights ? lights_pdf_value(S, rec.p, dir) : cos_pdf;
-          const double pdf_val = 0.5 * p0 + 0.5 * cos_pdf;
-          if (!isfinite(pdf_val) || pdf_val <= 0.0) {
-            terminal = emitted;
-          } else {
-            const double cs = dot(rec.normal, unit_vector(dir));
-            const double spdf = cs < 0.0 ? 0.0 : cs / kPi;
-            thr = thr * atten * spdf / pdf_val;
-            next_o = rec.p;
-            next_d = dir;
-            done = false;
-          }
-        }
-      }
-      if (!done && bounce >= R.max_depth) { // depth exhausted: ray_reflectance(depth 0) = 1.0
-        done = true;
-        terminal = 1.0;
-      }
-      if (done) {
-        const double refl = thr * terminal;
-        double cie[3];
-        xyz_from_wavelength(S, wl, cie);
-        R.st.contrib[(size_t)id * 3 + 0] = cie[0] * refl;
-        R.st.contrib[(size_t)id * 3 + 1] = cie[1] * refl;
-        R.st.contrib[(size_t)id * 3 + 2] = cie[2] * refl;
-      } else {
-        yart_ray nr;
-        nr.origin[0] = next_o.x; nr.origin[1] = next_o.y; nr.origin[2] = next_o.z;
-        nr.direction[0] = next_d.x; nr.direction[1] = next_d.y; nr.direction[2] = next_d.z;
-        R.st.rays[id] = nr;
-        R.st.throughput[id] = thr;
-        alive = true;
-      }
+      alive = shade_path(R, id, bounce);
     }
     // stream compaction: one atomic per warp
     const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
