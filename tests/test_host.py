@@ -3,6 +3,7 @@ include/yart.h declares, the OBJ front end and the QBVH flattening agree with in
 restatements, presets carry the reference's values, and compute calls fail loudly without a GPU.
 No compute calls are made here."""
 import ctypes as C
+import importlib
 import os
 import re
 from pathlib import Path
@@ -212,3 +213,45 @@ def test_cli_parses_like_the_reference():  # main.rs:831-842 and parse_positive_
     for bad in (["--scene", "not-a-scene"], ["--scene", "david", "--samples", "0"], ["--scene", "david", "--width", "-3"], []):
         with pytest.raises(SystemExit):
             p.parse_args(bad)
+
+
+def test_rust_sys_crate_source_matches_the_header(yart):
+    """bindings/rust/yart-sys cannot be compiled here (no Rust toolchain), so keep it honest textually: it declares
+    exactly the functions of yart.h, and its #[repr(C)] structs list the same fields in the same order as the
+    ctypes structs the tests run with (sizes of the Rust scalar types give the same struct sizes)."""
+    src = (ROOT / "bindings" / "rust" / "yart-sys" / "src" / "lib.rs").read_text()
+    header = (ROOT / "include" / "yart.h").read_text()
+    declared = set(re.findall(r"\b(yart_[a-z_0-9]+)\s*\(", header)) - {"yart_status"}
+    rust_fns = set(re.findall(r"pub fn (yart_[a-z_0-9]+)\s*\(", src))
+    assert rust_fns == declared
+    abi = importlib.import_module("yet-another-raytracer_b200._abi")
+    pairs = {"yart_trimesh": abi.Trimesh, "yart_object": abi.Object, "yart_group": abi.Group, "yart_material": abi.Material,
+             "yart_texture": abi.Texture, "yart_perlin": abi.Perlin, "yart_image": abi.Image, "yart_scene_desc": abi.SceneDesc,
+             "yart_camera": abi.Camera, "yart_stats": abi.Stats, "yart_render_opts": abi.RenderOpts,
+             "yart_qbvh_info": abi.QbvhInfo, "yart_preset_info": abi.PresetInfo}
+    scalar = {"u8": 1, "u32": 4, "i32": 4, "u64": 8, "f32": 4, "f64": 8, "c_char": 1}
+
+    def size_of(ty):
+        ty = ty.strip()
+        if ty.startswith("*"):
+            return 8, 8
+        m = re.fullmatch(r"\[(.+);\s*(\d+)\]", ty)
+        if m:
+            s, a = size_of(m.group(1))
+            return s * int(m.group(2)), a
+        return scalar[ty], scalar[ty]
+
+    for name, cls in pairs.items():
+        m = re.search(r"pub struct %s \{(.*?)\n?\}" % name, src, re.S)
+        assert m, name
+        fields = re.findall(r"pub (\w+):\s*([^,}]+?)\s*(?:,|$)", m.group(1).replace("\n", " "))
+        assert [f for f, _ in fields] == [f for f, _ in cls._fields_], name
+        off = 0
+        align = 1
+        for _, ty in fields:  # C layout rules
+            s, a = size_of(ty)
+            off = (off + a - 1) // a * a + s
+            align = max(align, a)
+        assert (off + align - 1) // align * align == C.sizeof(cls), name
+    for name, size in (("yart_ray", 48), ("yart_hit", 40)):
+        assert re.search(r"pub struct %s \{" % name, src)
