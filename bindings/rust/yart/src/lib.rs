@@ -1,0 +1,98 @@
+//! Safe wrapper over `yart-sys` -- what the reference (raytracer/src/) would depend on.  NOT compiled in the
+//! repository's build environment (no Rust toolchain there).
+//!
+//! `GpuScene` plays the part of `world: Arc<HittableList>` (main.rs:434-446): `hit` has the shape of
+//! `Hittable::hit(&self, &Ray, t_min, t_max) -> Option<HitRecord>` (hittable.rs:24) for drop-in testing, `hit_many`
+//! is the batched form the GPU is for, `render` replaces the tile loop of `render()` (main.rs:629-760).
+use std::ffi::{CStr, CString};
+use std::ptr;
+use yart_sys as sys;
+
+#[derive(Debug)]
+pub struct Error { pub code: i32, pub message: String }
+pub type Result<T> = std::result::Result<T, Error>;
+
+#[derive(Clone, Copy, Debug)]
+pub struct Ray { pub origin: [f64; 3], pub direction: [f64; 3] }
+
+/// The part of the reference's `HitRecord` the closest-hit query returns (the shade stage rebuilds the rest).
+#[derive(Clone, Copy, Debug)]
+pub struct Hit { pub t: f64, pub u: f64, pub v: f64, pub prim_id: u32, pub obj_id: u32, pub front_face: bool }
+
+pub struct GpuScene { ctx: *mut sys::yart_ctx, preset: *mut sys::yart_preset }
+
+// One context per host thread (yart.h); the scene itself is immutable after construction like the reference's
+// `Hittable: Send + Sync` objects, but calls go through the context, so no `Sync`.
+unsafe impl Send for GpuScene {}
+
+impl GpuScene {
+    fn ctx_err(&self, code: i32) -> Error {
+        let message = unsafe { CStr::from_ptr(sys::yart_last_error(self.ctx)) }.to_string_lossy().into_owned();
+        Error { code, message }
+    }
+    fn global_err(code: i32) -> Error {
+        let message = unsafe { CStr::from_ptr(sys::yart_last_error_global()) }.to_string_lossy().into_owned();
+        Error { code, message }
+    }
+
+    /// `build_scene_preset` (main.rs:211-432) on GPU `device`; `name` is the kebab-case `--scene` value.
+    pub fn from_preset(name: &str, assets_dir: &str, seed: u64, device: i32) -> Result<GpuScene> {
+        let (name, assets) = (CString::new(name).unwrap(), CString::new(assets_dir).unwrap());
+        let mut s = GpuScene { ctx: ptr::null_mut(), preset: ptr::null_mut() };
+        unsafe {
+            let rc = sys::yart_preset_build(name.as_ptr(), assets.as_ptr(), seed, &mut s.preset);
+            if rc != 0 { return Err(Self::global_err(rc)); }
+            let rc = sys::yart_ctx_create(device, &mut s.ctx);
+            if rc != 0 { return Err(Self::global_err(rc)); } // no CPU fallback: YART_ERR_CUDA without a B200
+            let rc = sys::yart_ctx_set_scene(s.ctx, sys::yart_preset_scene(s.preset));
+            if rc != 0 { return Err(s.ctx_err(rc)); }
+        }
+        Ok(s)
+    }
+
+    /// Batched `world.hit(ray, t_min, t_max)` (main.rs:548): one result per ray, `None` = miss.
+    pub fn hit_many(&self, rays: &[Ray], t_min: f64, t_max: f64) -> Result<Vec<Option<Hit>>> {
+        let raw: Vec<sys::yart_ray> = rays.iter().map(|r| sys::yart_ray { origin: r.origin, direction: r.direction }).collect();
+        let mut hits = vec![sys::yart_hit { t: 0.0, u: 0.0, v: 0.0, prim_id: 0, obj_id: 0, front_face: 0, _pad: 0 }; rays.len()];
+        let rc = unsafe {
+            sys::yart_closest_hit(self.ctx, sys::YART_TARGET_WORLD, raw.as_ptr(), raw.len() as u64, t_min, t_max,
+                                  sys::YART_ORDER_NEAR, 0, hits.as_mut_ptr(), ptr::null_mut())
+        };
+        if rc != 0 { return Err(self.ctx_err(rc)); }
+        Ok(hits.iter().map(|h| if h.obj_id == sys::YART_MISS { None } else {
+            Some(Hit { t: h.t, u: h.u, v: h.v, prim_id: h.prim_id, obj_id: h.obj_id, front_face: h.front_face != 0 })
+        }).collect())
+    }
+
+    /// `Hittable::hit` for a single ray (hittable.rs:24) -- for drop-in tests; use `hit_many` for work.
+    pub fn hit(&self, ray: &Ray, t_min: f64, t_max: f64) -> Option<Hit> {
+        self.hit_many(std::slice::from_ref(ray), t_min, t_max).ok().and_then(|mut v| v.pop().flatten())
+    }
+
+    /// `render()` (main.rs:590-775) up to the RGBA8 image; samples `[0, spp)` of every pixel.
+    pub fn render(&self, width: u32, height: u32, spp: u32, max_depth: u32, seed: u64) -> Result<Vec<u8>> {
+        let mut cam: sys::yart_camera = unsafe { std::mem::zeroed() };
+        let rc = unsafe { sys::yart_preset_camera(self.preset, width, height, -1.0, -1.0, &mut cam) };
+        if rc != 0 { return Err(Self::global_err(rc)); }
+        let opts = sys::yart_render_opts { width, height, sample_begin: 0, sample_end: spp, max_depth,
+                                           order: sys::YART_ORDER_NEAR, seed, ..Default::default() };
+        let mut film = vec![0f64; (width as usize) * (height as usize) * 3];
+        let mut rgba = vec![0u8; (width as usize) * (height as usize) * 4];
+        unsafe {
+            let rc = sys::yart_render(self.ctx, &cam, &opts, film.as_mut_ptr(), ptr::null_mut());
+            if rc != 0 { return Err(self.ctx_err(rc)); }
+            let rc = sys::yart_film_finalize(self.ctx, film.as_ptr(), width, height, spp, 0, rgba.as_mut_ptr());
+            if rc != 0 { return Err(self.ctx_err(rc)); }
+        }
+        Ok(rgba)
+    }
+}
+
+impl Drop for GpuScene {
+    fn drop(&mut self) {
+        unsafe {
+            if !self.ctx.is_null() { sys::yart_ctx_destroy(self.ctx); }
+            if !self.preset.is_null() { sys::yart_preset_free(self.preset); }
+        }
+    }
+}
