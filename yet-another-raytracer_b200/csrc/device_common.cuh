@@ -131,6 +131,8 @@ struct DevMesh {
   const float4* nodes;  // 8 float4 per node (host_common.h FlatNode: x, y, z slab pairs, children)
   const float4* tris;   // 3 float4 per triangle, tree order (FlatTri)
   const double* shade;  // 12 doubles per triangle (FlatTriShade: 9 normals + 6 float uvs)
+  const float4* leafgeo; // per leaf, at 64 B x (its first triangle's position): the 9 vertex floats of each of
+                         // its triangles back to back (36 B per triangle) -- a 3-triangle leaf is 4 sectors
   uint32_t root;
   uint32_t max_stack;
   uint32_t n_nodes, n_tris;

@@ -277,6 +277,7 @@ struct TraverseParams {
   PassCommon c;
   const float4* nodes;
   const float4* tris;
+  const float4* leafgeo;      // packed per-leaf vertex blocks (DevMesh::leafgeo)
   uint32_t root;
   uint32_t obj_index;         // world object index recorded with a hit
   uint32_t wrap;              // YART_WRAP_ROTATE_Y / TRANSLATE of this instance
@@ -651,43 +652,67 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
       const uint32_t first = cur & 0x7FFFFFFu;
       if (COUNT) n_tris += count;
       YART_CHECK(count >= 1 && count <= 4 && first + count <= P.n_tris);
-      // the next triangle's record is requested before the current one is tested (its ~100 dependent f64
-      // instructions then cover the fetch)
-      float4 n0, n1, n2;
-      {
-        const float4* tp = tris + (size_t)(first + (NEAR ? (count - 1u) : 0u)) * 3;
-        n0 = __ldg(tp); n1 = __ldg(tp + 1); n2 = __ldg(tp + 2);
-      }
-      for (uint32_t j = 0; j < count; ++j) {
-        const uint32_t i = NEAR ? (count - 1u - j) : j;
-        const float4 a0 = n0, a1 = n1, a2 = n2;
-        if (j + 1u < count) {
-          const float4* tp = tris + (size_t)(first + (NEAR ? (i - 1u) : (i + 1u))) * 3;
+      // Moeller-Trumbore exactly as qbvh.rs:419-489 on one triangle given as 9 floats
+#define YART_TRI_TEST(I_, F0, F1, F2, F3, F4, F5, F6, F7, F8)                                                       \
+  {                                                                                                                 \
+    const double v0x = (double)(F0), v0y = (double)(F1), v0z = (double)(F2);                                        \
+    const double e1x = (double)(F3) - v0x, e1y = (double)(F4) - v0y, e1z = (double)(F5) - v0z;                      \
+    const double e2x = (double)(F6) - v0x, e2y = (double)(F7) - v0y, e2z = (double)(F8) - v0z;                      \
+    const double hx = dy * e2z - dz * e2y, hy = dz * e2x - dx * e2z, hz = dx * e2y - dy * e2x;                      \
+    const double a = e1x * hx + e1y * hy + e1z * hz;                                                                \
+    bool ok = !((a > -kF64Eps) && (a < kF64Eps));                                                                   \
+    const double f = 1.0 / a;                                                                                       \
+    const double sx = ox - v0x, sy = oy - v0y, sz = oz - v0z;                                                       \
+    const double u = f * (sx * hx + sy * hy + sz * hz);                                                             \
+    ok = ok && (u >= 0.0) && (u <= 1.0);                                                                            \
+    const double qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;                      \
+    const double v = f * (dx * qx + dy * qy + dz * qz);                                                             \
+    ok = ok && (v >= 0.0) && ((u + v) <= 1.0);                                                                      \
+    const double t = f * (e2x * qx + e2y * qy + e2z * qz);                                                          \
+    ok = ok && (t >= t_min);                                                                                        \
+    /* REFERENCE: first found wins (`t_max > t`, qbvh.rs:478).  NEAR: mirrored -- last found wins among this */    \
+    /* mesh's equal-t hits, still strictly closer than what earlier objects left.                            */    \
+    ok = ok && (NEAR ? ((t <= t_best) && (t < t_entry)) : (t_best > t));                                            \
+    if (ok) {                                                                                                       \
+      t_best = t; best_prim = first + (I_); best_bu = u; best_bv = v;                                               \
+      if (MIXED) t_best_f = (float)t;                                                                               \
+    }                                                                                                               \
+  }
+      if (count <= 3u) {
+        // The leaf's triangles as one packed block (36 B each, 32-byte aligned): 2 / 3 / 4 sector loads for
+        // 1 / 2 / 3 triangles instead of 3 loads per triangle, all in flight together.
+        const float4* lp = P.leafgeo + (size_t)first * 4;
+        F8 s0 = ldg256(lp), s1 = ldg256(lp + 2), s2, s3;
+        s2.lo = s2.hi = s3.lo = s3.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (count >= 2u) s2 = ldg256(lp + 4);
+        if (count >= 3u) s3 = ldg256(lp + 6);
+        if (NEAR) { // lanes in reverse order (mirrored tie rule)
+          if (count >= 3u) YART_TRI_TEST(2u, s2.lo.z, s2.lo.w, s2.hi.x, s2.hi.y, s2.hi.z, s2.hi.w, s3.lo.x, s3.lo.y, s3.lo.z)
+          if (count >= 2u) YART_TRI_TEST(1u, s1.lo.y, s1.lo.z, s1.lo.w, s1.hi.x, s1.hi.y, s1.hi.z, s1.hi.w, s2.lo.x, s2.lo.y)
+          YART_TRI_TEST(0u, s0.lo.x, s0.lo.y, s0.lo.z, s0.lo.w, s0.hi.x, s0.hi.y, s0.hi.z, s0.hi.w, s1.lo.x)
+        } else {
+          YART_TRI_TEST(0u, s0.lo.x, s0.lo.y, s0.lo.z, s0.lo.w, s0.hi.x, s0.hi.y, s0.hi.z, s0.hi.w, s1.lo.x)
+          if (count >= 2u) YART_TRI_TEST(1u, s1.lo.y, s1.lo.z, s1.lo.w, s1.hi.x, s1.hi.y, s1.hi.z, s1.hi.w, s2.lo.x, s2.lo.y)
+          if (count >= 3u) YART_TRI_TEST(2u, s2.lo.z, s2.lo.w, s2.hi.x, s2.hi.y, s2.hi.z, s2.hi.w, s3.lo.x, s3.lo.y, s3.lo.z)
+        }
+      } else {
+        // 4-triangle leaves: one 48-byte record at a time, the next one requested before the current is tested
+        float4 n0, n1, n2;
+        {
+          const float4* tp = tris + (size_t)(first + (NEAR ? (count - 1u) : 0u)) * 3;
           n0 = __ldg(tp); n1 = __ldg(tp + 1); n2 = __ldg(tp + 2);
         }
-        const double v0x = (double)a0.x, v0y = (double)a0.y, v0z = (double)a0.z;
-        const double e1x = (double)a1.x - v0x, e1y = (double)a1.y - v0y, e1z = (double)a1.z - v0z;
-        const double e2x = (double)a2.x - v0x, e2y = (double)a2.y - v0y, e2z = (double)a2.z - v0z;
-        const double hx = dy * e2z - dz * e2y, hy = dz * e2x - dx * e2z, hz = dx * e2y - dy * e2x;
-        const double a = e1x * hx + e1y * hy + e1z * hz;
-        bool ok = !((a > -kF64Eps) && (a < kF64Eps));
-        const double f = 1.0 / a;
-        const double sx = ox - v0x, sy = oy - v0y, sz = oz - v0z;
-        const double u = f * (sx * hx + sy * hy + sz * hz);
-        ok = ok && (u >= 0.0) && (u <= 1.0);
-        const double qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
-        const double v = f * (dx * qx + dy * qy + dz * qz);
-        ok = ok && (v >= 0.0) && ((u + v) <= 1.0);
-        const double t = f * (e2x * qx + e2y * qy + e2z * qz);
-        ok = ok && (t >= t_min);
-        // REFERENCE: first found wins (`t_max > t`, qbvh.rs:478).  NEAR: mirrored -- last found wins
-        // among this mesh's equal-t hits, still strictly closer than what earlier objects left.
-        ok = ok && (NEAR ? ((t <= t_best) && (t < t_entry)) : (t_best > t));
-        if (ok) {
-          t_best = t; best_prim = first + i; best_bu = u; best_bv = v;
-          if (MIXED) t_best_f = (float)t;
+        for (uint32_t j = 0; j < count; ++j) {
+          const uint32_t i = NEAR ? (count - 1u - j) : j;
+          const float4 a0 = n0, a1 = n1, a2 = n2;
+          if (j + 1u < count) {
+            const float4* tp = tris + (size_t)(first + (NEAR ? (i - 1u) : (i + 1u))) * 3;
+            n0 = __ldg(tp); n1 = __ldg(tp + 1); n2 = __ldg(tp + 2);
+          }
+          YART_TRI_TEST(i, a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, a2.x, a2.y, a2.z)
         }
       }
+#undef YART_TRI_TEST
       if (sp == 0) {
         cur = kSentinel;
       } else {

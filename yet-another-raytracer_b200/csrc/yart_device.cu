@@ -57,6 +57,26 @@ __global__ void __launch_bounds__(256) k_export(const DevScene S, const yart_ray
   }
 }
 
+// DevMesh::leafgeo from the flattened tree: one thread per (node, child); a leaf child's triangles are copied
+// vertex by vertex (9 floats each) to 64 B x (position of its first triangle)
+__global__ void __launch_bounds__(256) k_pack_leaves(const FlatNode* __restrict__ nodes, uint32_t n_nodes, const FlatTri* __restrict__ tris,
+                                                      float* __restrict__ leafgeo) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_nodes * 4u) return;
+  const uint32_t id = nodes[w >> 2].child[w & 3u];
+  if (id == 0xFFFFFFFFu || !(id >> 31)) return;
+  const uint32_t count = (id >> 27) & 0xFu, first = id & 0x7FFFFFFu;
+  float* out = leafgeo + (size_t)first * 16;
+  for (uint32_t i = 0; i < count; ++i) {
+    const FlatTri& t = tris[first + i];
+    for (int j = 0; j < 3; ++j) {
+      out[i * 9 + j] = t.v0[j];
+      out[i * 9 + 3 + j] = t.v1[j];
+      out[i * 9 + 6 + j] = t.v2[j];
+    }
+  }
+}
+
 // yart_measure_fetch_peak: independent random 128-byte line fetches (one QBVH node visit = four LDG.E.256)
 template <int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_fetch_peak(const float4* __restrict__ table, uint32_t n_lines, uint32_t iters,
@@ -376,6 +396,7 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       T.c.first_pass = first ? 1u : 0u;
       T.nodes = m.nodes;
       T.tris = m.tris;
+      T.leafgeo = m.leafgeo;
       T.root = m.root;
       T.n_nodes = m.n_nodes;
       T.n_tris = m.n_tris;
@@ -654,6 +675,15 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
     meshes[i].nodes = reinterpret_cast<const float4*>(dn);
     meshes[i].tris = reinterpret_cast<const float4*>(dt);
     meshes[i].shade = reinterpret_cast<const double*>(ds);
+    {
+      float* dl = nullptr; // 64 B per triangle position; only the first 36 B x count of a leaf's block are used
+      CUDA_TRY(ctx, cudaMalloc((void**)&dl, (size_t)q.n_tris * 64));
+      ctx->scene_allocs.push_back(dl);
+      CUDA_TRY(ctx, cudaMemsetAsync(dl, 0, (size_t)q.n_tris * 64, ctx->stream));
+      k_pack_leaves<<<(q.n_nodes * 4u + 255u) / 256u, 256, 0, ctx->stream>>>(dn, q.n_nodes, dt, dl);
+      CUDA_TRY(ctx, cudaGetLastError());
+      meshes[i].leafgeo = reinterpret_cast<const float4*>(dl);
+    }
     meshes[i].root = q.root;
     meshes[i].max_stack = q.max_stack;
     meshes[i].n_nodes = q.n_nodes;
