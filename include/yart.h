@@ -337,7 +337,8 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* scene);
  * target = mesh index: L4QBVH::hit (qbvh.rs:381-543) on that mesh alone;
  * target = YART_TARGET_WORLD: HittableList::hit (hittable.rs:66-79) over the whole world
  *   (constant media use the Philox stream of pixel=ray index, sample 0, bounce 1).
- * rays/hits: n elements, host pointers unless YART_FLAG_DEVICE_PTRS. */
+ * rays/hits: n elements, host pointers unless YART_FLAG_DEVICE_PTRS (device ray arrays must be 16-byte
+ * aligned, which every cudaMalloc'ed array is). */
 int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint64_t n,
                      double t_min, double t_max, uint32_t order, uint32_t flags,
                      yart_hit* hits, yart_stats* stats /* may be NULL */);

@@ -170,6 +170,21 @@ struct DevScene {
   double background[3];
 };
 
+// A 48-byte ray record as three 128-bit accesses instead of six 64-bit ones (half the L1 wavefronts).  Every
+// ray array of the library is 16-byte aligned (cudaMalloc; yart_closest_hit checks device pointers it is given).
+YART_DEV void load_ray(const yart_ray* p, D3& o, D3& d) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = q[0], b = q[1], c = q[2];
+  o = d3(a.x, a.y, b.x);
+  d = d3(b.y, c.x, c.y);
+}
+YART_DEV void store_ray(yart_ray* p, D3 o, D3 d) {
+  double2* q = reinterpret_cast<double2*>(p);
+  q[0] = make_double2(o.x, o.y);
+  q[1] = make_double2(o.z, d.x);
+  q[2] = make_double2(d.y, d.z);
+}
+
 // What a closest-hit query leaves behind for the shade stage (32 bytes).
 struct alignas(16) DevHit {
   double t;      // +inf on a miss

@@ -498,10 +498,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams R, uint32_t* 
         D3 ro, rd;
         double time, wl;
         camera_sample(R.cam, rng, px, py, R.width, R.height, ro, rd, time, wl);
-        yart_ray r;
-        r.origin[0] = ro.x; r.origin[1] = ro.y; r.origin[2] = ro.z;
-        r.direction[0] = rd.x; r.direction[1] = rd.y; r.direction[2] = rd.z;
-        R.st.rays[id] = r;
+        store_ray(R.st.rays + id, ro, rd);
         R.st.time[id] = time;
         R.st.wavelength[id] = wl;
         R.st.throughput[id] = 1.0;
@@ -555,9 +552,8 @@ YART_DEV bool shade_path(const RenderParams& R, uint32_t id, uint32_t bounce) {
   const uint32_t pixel = R.pixel_base + id / R.spp_batch;
   const uint32_t sample = R.sample_base + id % R.spp_batch;
   const Rng rng = make_rng(R.seed, pixel, sample);
-  const yart_ray wr = R.st.rays[id];
-  const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
-  const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+  D3 wo, wd;
+  load_ray(R.st.rays + id, wo, wd);
   const double time = R.st.time[id];
   const double wl = R.st.wavelength[id];
   double thr = R.st.throughput[id];
@@ -656,10 +652,7 @@ YART_DEV bool shade_path(const RenderParams& R, uint32_t id, uint32_t bounce) {
     R.st.contrib[(size_t)id * 3 + 1] = cie[1] * refl;
     R.st.contrib[(size_t)id * 3 + 2] = cie[2] * refl;
   } else {
-    yart_ray nr;
-    nr.origin[0] = next_o.x; nr.origin[1] = next_o.y; nr.origin[2] = next_o.z;
-    nr.direction[0] = next_d.x; nr.direction[1] = next_d.y; nr.direction[2] = next_d.z;
-    R.st.rays[id] = nr;
+    store_ray(R.st.rays + id, next_o, next_d);
     R.st.throughput[id] = thr;
     alive = true;
   }
@@ -693,9 +686,8 @@ __global__ void __launch_bounds__(kShadeThreads, YART_SHADE_MIN_BLOCKS) k_shade(
         uint32_t obj = R.st.hits[my_id].obj;
         if (R.tail_end > R.tail_begin) {
           // the last objects of HittableList::hit's scan (hittable.rs:66-79), same calls as k_analytic makes
-          const yart_ray wr = R.st.rays[my_id];
-          const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
-          const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+          D3 wo, wd;
+          load_ray(R.st.rays + my_id, wo, wd);
           double t_best = R.st.hits[my_id].t; // (+inf on a miss; t_max of the scan is +inf, main.rs:548)
           bool changed = false;
           for (uint32_t oi = R.tail_begin; oi < R.tail_end; ++oi) {

@@ -487,10 +487,9 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
         {
           ray_id = new_id;
           YART_CHECK(ray_id < P.c.n_rays);
-          const yart_ray wr = P.c.rays[ray_id];
+          D3 ro, rd;
+          load_ray(P.c.rays + ray_id, ro, rd);
           t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
-          D3 ro = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
-          D3 rd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
           // ray into the instance's space (hittable.rs:137-143, 218-227); uniform across the launch
           if (P.wrap & YART_WRAP_TRANSLATE) ro = ro - d3(P.offset[0], P.offset[1], P.offset[2]);
           if (P.wrap & YART_WRAP_ROTATE_Y) {
@@ -736,9 +735,8 @@ __global__ void __launch_bounds__(256) k_analytic(const AnalyticParams P) {
   for (uint64_t item = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; item < n; item += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
     YART_CHECK(ray_id < P.c.n_rays);
-    const yart_ray wr = P.c.rays[ray_id];
-    const D3 wo = d3(wr.origin[0], wr.origin[1], wr.origin[2]);
-    const D3 wd = d3(wr.direction[0], wr.direction[1], wr.direction[2]);
+    D3 wo, wd;
+    load_ray(P.c.rays + ray_id, wo, wd);
     DevHit h;
     if (P.c.first_pass) {
       h.t = d_inf(); h.bu = 0.0; h.bv = 0.0; h.obj = YART_MISS; h.prim = 0;

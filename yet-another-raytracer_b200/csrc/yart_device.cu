@@ -816,6 +816,10 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
     ctx->err = "yart_closest_hit: bad argument";
     return YART_ERR_INVALID;
   }
+  if ((flags & YART_FLAG_DEVICE_PTRS) && ((reinterpret_cast<uintptr_t>(rays) & 15u) || (reinterpret_cast<uintptr_t>(hits) & 7u))) {
+    ctx->err = "yart_closest_hit: device ray arrays must be 16-byte aligned (hits: 8)";
+    return YART_ERR_INVALID;
+  }
   if (target != YART_TARGET_WORLD && target >= ctx->n_meshes) {
     ctx->err = "yart_closest_hit: target is neither a mesh index nor YART_TARGET_WORLD";
     return YART_ERR_INVALID;
