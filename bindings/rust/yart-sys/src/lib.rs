@@ -45,10 +45,15 @@ pub const YART_ORDER_REFERENCE: u32 = 0;
 pub const YART_ORDER_NEAR: u32 = 1;
 pub const YART_FLAG_DEVICE_PTRS: u32 = 1;
 pub const YART_FLAG_COUNT_VISITS: u32 = 2;
+pub const YART_FLAG_UNBIASED_LIGHT_PICK: u32 = 4;
+pub const YART_FLAG_RUSSIAN_ROULETTE: u32 = 8;
+pub const YART_FLAG_DEPTH_ZERO_BLACK: u32 = 16;
+pub const YART_COMM_ID_BYTES: usize = 128;
 pub const YART_BUILDER_HOST: u32 = 0;
 pub const YART_BUILDER_DEVICE: u32 = 1;
 
 #[repr(C)] pub struct yart_ctx { _private: [u8; 0] }
+#[repr(C)] pub struct yart_comm { _private: [u8; 0] }
 #[repr(C)] pub struct yart_preset { _private: [u8; 0] }
 #[repr(C)] pub struct yart_objfile { _private: [u8; 0] }
 #[repr(C)] pub struct yart_qbvh { _private: [u8; 0] }
@@ -106,6 +111,12 @@ pub struct yart_camera {
 pub struct yart_ray { pub origin: [f64; 3], pub direction: [f64; 3] }
 
 #[repr(C)] #[derive(Clone, Copy)]
+pub struct yart_ray_f32 { pub origin: [f32; 3], pub direction: [f32; 3] }
+
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct yart_hit_f32 { pub t: f32, pub u: f32, pub v: f32, pub prim_id: u32 }
+
+#[repr(C)] #[derive(Clone, Copy)]
 pub struct yart_hit { pub t: f64, pub u: f64, pub v: f64, pub prim_id: u32, pub obj_id: u32, pub front_face: u32, pub _pad: u32 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -147,6 +158,7 @@ extern "C" {
     pub fn yart_qbvh_shade(q: *const yart_qbvh) -> *const c_void;
     pub fn yart_preset_build(name: *const c_char, assets_dir: *const c_char, seed: u64, out: *mut *mut yart_preset) -> c_int;
     pub fn yart_preset_free(p: *mut yart_preset);
+    pub fn yart_preset_note(p: *const yart_preset) -> *const c_char;
     pub fn yart_preset_scene(p: *const yart_preset) -> *const yart_scene_desc;
     pub fn yart_preset_get_info(p: *const yart_preset, out: *mut yart_preset_info) -> c_int;
     pub fn yart_preset_count() -> c_int;
@@ -165,12 +177,29 @@ extern "C" {
     pub fn yart_ctx_set_scene(ctx: *mut yart_ctx, scene: *const yart_scene_desc) -> c_int;
     pub fn yart_closest_hit(ctx: *mut yart_ctx, target: u32, rays: *const yart_ray, n: u64, t_min: f64, t_max: f64,
                             order: u32, flags: u32, hits: *mut yart_hit, stats: *mut yart_stats) -> c_int;
+    pub fn yart_closest_hit_f32(ctx: *mut yart_ctx, target: u32, rays: *const yart_ray_f32, n: u64, t_min: f32, t_max: f32,
+                                order: u32, flags: u32, hits: *mut yart_hit_f32, stats: *mut yart_stats) -> c_int;
     pub fn yart_render(ctx: *mut yart_ctx, camera: *const yart_camera, opts: *const yart_render_opts, film_xyz: *mut f64,
                        stats: *mut yart_stats) -> c_int;
     pub fn yart_film_finalize(ctx: *mut yart_ctx, film_xyz: *const f64, width: u32, height: u32, spp: u32, flags: u32,
                               rgba8: *mut u8) -> c_int;
     pub fn yart_generate_camera_rays(ctx: *mut yart_ctx, camera: *const yart_camera, opts: *const yart_render_opts,
                                      rays_host: *mut yart_ray, wavelength_host: *mut f64, time_host: *mut f64) -> c_int;
+    pub fn yart_dump_path_rays(ctx: *mut yart_ctx, camera: *const yart_camera, opts: *const yart_render_opts,
+                               rays: *mut yart_ray, cap: u64, n_out: *mut u64) -> c_int;
     pub fn yart_measure_fetch_peak(ctx: *mut yart_ctx, table_bytes: u64, fetches_per_thread: u32, mode: u32,
                                    gbytes_per_s: *mut f64) -> c_int;
+    // multi-GPU: sample-range sharding + one in-place NCCL reduce of the f64 film (replaces main.rs:746-760)
+    pub fn yart_comm_unique_id(id: *mut u8) -> c_int; // YART_COMM_ID_BYTES bytes
+    pub fn yart_comm_init_rank(ctx: *mut yart_ctx, id: *const u8, rank: c_int, n_ranks: c_int, out: *mut *mut yart_comm) -> c_int;
+    pub fn yart_comm_init(ctxs: *const *mut yart_ctx, n: c_int, out: *mut *mut yart_comm) -> c_int;
+    pub fn yart_comm_destroy(comm: *mut yart_comm);
+    pub fn yart_comm_info(comm: *const yart_comm, n_ranks: *mut c_int, n_local: *mut c_int, first_local_rank: *mut c_int,
+                          nccl_version: *mut c_int) -> c_int;
+    pub fn yart_comm_last_error(comm: *const yart_comm) -> *const c_char;
+    pub fn yart_film_reduce(comm: *mut yart_comm, dev_films: *const *mut f64, width: u32, height: u32, root: c_int) -> c_int;
+    pub fn yart_film_create(ctx: *mut yart_ctx, width: u32, height: u32, dev_film: *mut *mut f64) -> c_int;
+    pub fn yart_film_clear(ctx: *mut yart_ctx, dev_film: *mut f64, width: u32, height: u32) -> c_int;
+    pub fn yart_film_read(ctx: *mut yart_ctx, dev_film: *const f64, width: u32, height: u32, host_film: *mut f64) -> c_int;
+    pub fn yart_film_destroy(ctx: *mut yart_ctx, dev_film: *mut f64);
 }

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YART_ABI_VERSION 1
+#define YART_ABI_VERSION 2
 
 typedef enum yart_status {
   YART_OK = 0,
@@ -206,6 +206,18 @@ typedef struct yart_hit {
   uint32_t _pad;
 } yart_hit;
 
+/* Single-precision ray / hit records for yart_closest_hit_f32: 24 + 16 bytes per ray instead of 48 + 40. */
+typedef struct yart_ray_f32 {
+  float origin[3];
+  float direction[3];
+} yart_ray_f32;
+
+typedef struct yart_hit_f32 {
+  float t;          /* +inf on a miss                                   */
+  float u, v;       /* as yart_hit.u / .v                               */
+  uint32_t prim_id; /* as yart_hit.prim_id; YART_MISS = miss            */
+} yart_hit_f32;
+
 /* Traversal order of the 4 children of a QBVH node.
  *  REFERENCE: exactly qbvh.rs:14-31,521-533 -- the ORDER_TABLE lookup, which visits the FAR
  *    child first; first-found wins among equal-t hits (qbvh.rs:478).
@@ -216,7 +228,16 @@ enum { YART_ORDER_REFERENCE = 0, YART_ORDER_NEAR = 1 };
 /* flags of yart_closest_hit / yart_render */
 enum {
   YART_FLAG_DEVICE_PTRS = 1u,   /* rays/hits (or the film) are device pointers on the ctx's GPU */
-  YART_FLAG_COUNT_VISITS = 2u   /* fill node/leaf visit counters in the stats (slower)          */
+  YART_FLAG_COUNT_VISITS = 2u,  /* fill node/leaf visit counters in the stats (slower)          */
+  /* Better sampling, yart_render only, OFF by default: with none of them set the renderer is the reference's
+   * estimator bit for bit. */
+  YART_FLAG_UNBIASED_LIGHT_PICK = 4u, /* pick among ALL lights; the reference's HittableList::random draws from
+                                         gen_range(0..len-1) and never samples the last one although pdf_value
+                                         averages over all of them (hittable.rs:113-122 vs :103-111)            */
+  YART_FLAG_RUSSIAN_ROULETTE = 8u,    /* from bounce 4 on a path survives with probability clamp(throughput, 0.05, 1)
+                                         and is reweighted by 1/q (unbiased; the reference has no roulette)      */
+  YART_FLAG_DEPTH_ZERO_BLACK = 16u    /* a path cut at max_depth contributes 0; the reference's ray_reflectance
+                                         returns 1.0 at depth 0 (main.rs:544-546)                                */
 };
 
 #define YART_TARGET_WORLD 0xFFFFFFFFu
@@ -283,9 +304,13 @@ const void* yart_qbvh_shade(const yart_qbvh* q); /* n_tris x 96 bytes: vertex no
 /* build_scene_preset (main.rs:211-432) + scenes.rs.  `name` is the reference's kebab-case
  * --scene value (main.rs:61-76).  `assets_dir` holds cube.obj / david.obj / sycee.obj /
  * earthmap_1024x512.rgb8.  `seed` replaces thread_rng for random-scene, next-week-final and
- * the Perlin tables.  Missing bunny.obj / teapot.obj are substituted by sycee.obj. */
+ * the Perlin tables.  bunny.obj / teapot.obj are not shipped with the reference: they are used when assets_dir has
+ * them; otherwise sycee.obj stands in and yart_preset_note() says so (with YART_STRICT_ASSETS=1 in the environment the
+ * call fails with YART_ERR_IO instead, like the reference's "Failed to load OBJ file", triangle.rs:112-113). */
 int yart_preset_build(const char* name, const char* assets_dir, uint64_t seed, yart_preset** out);
 void yart_preset_free(yart_preset* p);
+/* "" or a sentence the front end must show the user (a stand-in mesh was loaded).  Borrowed, valid until free. */
+const char* yart_preset_note(const yart_preset* p);
 const yart_scene_desc* yart_preset_scene(const yart_preset* p);
 
 typedef struct yart_preset_info { /* RenderDefaults + ScenePreset fields (main.rs:109-146) */
@@ -343,6 +368,14 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
                      double t_min, double t_max, uint32_t order, uint32_t flags,
                      yart_hit* hits, yart_stats* stats /* may be NULL */);
 
+/* The same query on single-precision records (SURVEY.md 8(b) "f32 variant too"; halves the ray / hit streams of the
+ * incoherent-ray sweep).  Each f32 ray is widened to f64 -- exactly -- and traced with the very same f64 arithmetic,
+ * so the hit is the one yart_closest_hit returns for the widened ray, with t, u, v rounded to nearest f32 and obj_id /
+ * front_face not reported.  Device ray arrays must be 8-byte aligned. */
+int yart_closest_hit_f32(yart_ctx* ctx, uint32_t target, const yart_ray_f32* rays, uint64_t n,
+                         float t_min, float t_max, uint32_t order, uint32_t flags,
+                         yart_hit_f32* hits, yart_stats* stats /* may be NULL */);
+
 /* Batched `render(config)` sample loop (main.rs:650-708) for samples
  * [sample_begin, sample_end): adds, per pixel and in sample order, the sanitised XYZ of each
  * sample (sanitize_sample_xyz main.rs:448-459) into film_xyz[height][width][3] (f64; host
@@ -363,6 +396,53 @@ int yart_generate_camera_rays(yart_ctx* ctx, const yart_camera* camera,
                               const yart_render_opts* opts, yart_ray* rays_host,
                               double* wavelength_host /* may be NULL */,
                               double* time_host /* may be NULL */);
+
+/* ------------------------------------------------------------------------------------ */
+/* Multi-GPU: sample-range sharding + one NCCL reduce of the film                       */
+/* ------------------------------------------------------------------------------------ */
+/* The reference shards its frame into 64 tiles over a thread pool and gathers them through an mpsc channel
+ * (main.rs:629-646, 746-760).  Here every GPU renders its own SAMPLE RANGE of every pixel (yart_render_opts
+ * sample_begin / sample_end; exact because sanitize_sample_xyz acts per sample, main.rs:700-707) into its own
+ * device-resident f64 film, and the films are summed onto the root with one ncclReduce over NVLink -- in place, on
+ * the context's stream, in the very buffer the render kernels accumulate into.  NCCL is loaded at run time
+ * (libnccl.so.2, or $YART_NCCL_LIB); without it these calls return YART_ERR_UNSUPPORTED.
+ *
+ *   one process per GPU (torchrun, MPI, N host processes of any kind):
+ *       rank 0: yart_comm_unique_id(id); ship the 128 bytes to the other ranks by any means;
+ *       every rank: yart_comm_init_rank(ctx, id, rank, n_ranks, &comm)
+ *   one process driving N GPUs (one host thread per context while rendering):
+ *       yart_comm_init(ctxs, n, &comm)
+ *   then, per frame:  yart_film_create / yart_film_clear -> yart_render(..., YART_FLAG_DEVICE_PTRS) with this rank's
+ *       sample range -> yart_film_reduce(comm, films, w, h, root) -> on the root: yart_film_finalize / yart_film_read. */
+typedef struct yart_comm yart_comm;
+#define YART_COMM_ID_BYTES 128
+
+int yart_comm_unique_id(uint8_t id[YART_COMM_ID_BYTES]);
+int yart_comm_init_rank(yart_ctx* ctx, const uint8_t id[YART_COMM_ID_BYTES], int rank, int n_ranks, yart_comm** out);
+int yart_comm_init(yart_ctx* const* ctxs, int n, yart_comm** out); /* rank i = ctxs[i]; all GPUs distinct */
+void yart_comm_destroy(yart_comm* comm);
+int yart_comm_info(const yart_comm* comm, int* n_ranks, int* n_local, int* first_local_rank, int* nccl_version);
+const char* yart_comm_last_error(const yart_comm* comm);
+
+/* dev_films: one device pointer per LOCAL rank (1 with yart_comm_init_rank, n with yart_comm_init), each a
+ * [height][width][3] f64 film on that rank's GPU.  root >= 0: the sum lands in root's film (the others keep their
+ * partial sums); root < 0: all-reduce.  Asynchronous on each context's stream. */
+int yart_film_reduce(yart_comm* comm, double* const* dev_films, uint32_t width, uint32_t height, int root);
+
+/* Device-resident films for hosts without CUDA of their own: zeroed on creation; pass them to yart_render /
+ * yart_film_finalize with YART_FLAG_DEVICE_PTRS. */
+int yart_film_create(yart_ctx* ctx, uint32_t width, uint32_t height, double** dev_film);
+int yart_film_clear(yart_ctx* ctx, double* dev_film, uint32_t width, uint32_t height);
+int yart_film_read(yart_ctx* ctx, const double* dev_film, uint32_t width, uint32_t height, double* host_film);
+void yart_film_destroy(yart_ctx* ctx, double* dev_film);
+
+/* The rays the renderer itself traces -- every `world.hit` of every path of samples [sample_begin, sample_end)
+ * (main.rs:548) -- in the order the closest-hit kernels see them: batch by batch, bounce by bounce, queue order within
+ * a bounce.  No film is produced.  rays: room for `cap` records (host, or device with YART_FLAG_DEVICE_PTRS in
+ * opts->flags); *n_out = the number of rays traced, which may exceed cap (only the first cap are stored).  For the
+ * "path-ray set" of the closest-hit sweep and for parity tests on the renderer's own ray distribution. */
+int yart_dump_path_rays(yart_ctx* ctx, const yart_camera* camera, const yart_render_opts* opts, yart_ray* rays,
+                        uint64_t cap, uint64_t* n_out);
 
 /* Roofline denominator for the closest-hit stage ("a measured L2 fetch peak"): every thread
  * fetches `fetches_per_thread` whole 128-byte lines (four 256-bit loads, like one QBVH node visit) at

@@ -31,6 +31,10 @@
                                       random_to_sphere (sphere.rs:11-21) or the XZRect point
                                       (aarect.rs:164-171: u0 -> x, u1 -> z)                          */
 #define YART_SLOT_DIELECTRIC 2u    /* u0 = reflect-vs-refract draw (material.rs:274)                */
+#define YART_SLOT_RR 3u            /* u0 = Russian-roulette survival draw (only with YART_FLAG_RUSSIAN_ROULETTE;
+                                      the reference has none)                                      */
+#define YART_RR_FIRST_BOUNCE 4u    /* roulette is played from this bounce on ...                    */
+#define YART_RR_MIN_SURVIVAL 0.05  /* ... with survival probability clamp(throughput, this, 1)      */
 #define YART_SLOT_SPHERE 0x100u    /* + 2*i, +2*i+1: i-th rejection iteration of
                                       random_in_unit_sphere (material.rs:308-324):
                                       x = 2*u0-1, y = 2*u1-1 (slot 2i), z = 2*u0-1 (slot 2i+1)      */

@@ -94,11 +94,11 @@ def _check(rc):
         raise RuntimeError("oracle error %d: %s" % (rc, lib().orc_last_error().decode()))
 
 
-def _opts(width, height, sample_begin, sample_end, max_depth, seed, order):
+def _opts(width, height, sample_begin, sample_end, max_depth, seed, order, flags=0):
     o = abi.RenderOpts()
     o.width, o.height = width, height
     o.sample_begin, o.sample_end = sample_begin, sample_end
-    o.max_depth, o.order, o.batch_spp, o.flags, o.seed = max_depth, order, 0, 0, seed
+    o.max_depth, o.order, o.batch_spp, o.flags, o.seed = max_depth, order, 0, flags, seed
     return o
 
 
@@ -154,11 +154,11 @@ class Scene:
         return ids[:min(n.value, 64)].copy()
 
     def render(self, camera, width, height, sample_begin, sample_end, max_depth=50, seed=1, order=abi.ORDER_REFERENCE,
-               n_threads=1, film=None, tiles=(0, 64)):
+               n_threads=1, film=None, tiles=(0, 64), flags=0):
         if film is None:
             film = np.zeros((height, width, 3), dtype=np.float64)
         st = abi.Stats()
-        o = _opts(width, height, sample_begin, sample_end, max_depth, seed, order)
+        o = _opts(width, height, sample_begin, sample_end, max_depth, seed, order, flags)
         _check(lib().orc_render_tiles(self._h, C.byref(camera), C.byref(o), film.ctypes.data, C.byref(st), n_threads,
                                       tiles[0], tiles[1]))
         return film, st

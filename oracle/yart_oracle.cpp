@@ -957,12 +957,14 @@ double lights_pdf_value(const Scene& s, V3 origin, V3 direction) { // hittable.r
   for (size_t i = 0; i < s.lights.size(); ++i) sum += weight * light_pdf_value(s.lights[i], origin, direction);
   return sum;
 }
-V3 lights_random(const Scene& s, V3 origin, double u_pick, double r1, double r2) { // hittable.rs:113-122
+// hittable.rs:113-122.  unbiased = YART_FLAG_UNBIASED_LIGHT_PICK (not the reference): uniform over all lights.
+V3 lights_random(const Scene& s, V3 origin, double u_pick, double r1, double r2, bool unbiased) {
   size_t n = s.lights.size();
   if (n == 0) return v3(1.0, 0.0, 0.0);
   if (n == 1) return light_random(s.lights[0], origin, r1, r2);
-  size_t k = (size_t)(u_pick * (double)(n - 1)); // gen_range(0..len-1): never the last light
-  if (k > n - 2) k = n - 2;
+  size_t m = unbiased ? n : n - 1;               // gen_range(0..len-1): never the last light
+  size_t k = (size_t)(u_pick * (double)m);
+  if (k > m - 1) k = m - 1;
   return light_random(s.lights[k], origin, r1, r2);
 }
 
@@ -1001,15 +1003,32 @@ inline double sellmeier_index(const yart_material& m, double wl) { // material.r
 struct Factor {
   double atten, spdf, pdf;
   bool diffuse;
+  bool roulette = false; // (flag only) atten holds the survival probability q: L = L / q
 };
 
 // ray_reflectance (main.rs:537-588), unrolled into a loop that records the per-bounce factors
 // and then folds them innermost-first so the multiplication order equals the recursion's.
+// `flags`: the better-sampling switches of yart_render_opts (YART_FLAG_UNBIASED_LIGHT_PICK / RUSSIAN_ROULETTE /
+// DEPTH_ZERO_BLACK); 0 = the reference's estimator.
 double ray_reflectance(const HitCtx& c, Ray ray, const Rng& rng, uint32_t max_depth, uint32_t* n_rays,
-                       std::vector<Factor>& factors, std::vector<yart_ray>* dump) {
+                       std::vector<Factor>& factors, std::vector<yart_ray>* dump, uint32_t flags = 0) {
   const Scene& s = *c.s;
   factors.clear();
-  double terminal = 1.0; // depth == 0 returns 1.0 (main.rs:544-546)
+  double terminal = (flags & YART_FLAG_DEPTH_ZERO_BLACK) ? 0.0 : 1.0; // depth == 0 returns 1.0 (main.rs:544-546)
+  double run = 1.0; // running throughput, front to back like the device's: only the roulette looks at it
+  bool cut = false;
+  auto roulette = [&](uint32_t bounce) { // after a scattering bounce; true = the path was cut
+    if (!(flags & YART_FLAG_RUSSIAN_ROULETTE) || bounce < YART_RR_FIRST_BOUNCE) return false;
+    const double q = run < YART_RR_MIN_SURVIVAL ? YART_RR_MIN_SURVIVAL : (run > 1.0 ? 1.0 : run);
+    double u_rr, unused;
+    rng.draw(bounce, YART_SLOT_RR, u_rr, unused);
+    if (u_rr >= q) return true;
+    run = run / q;
+    Factor f{q, 0, 0, false};
+    f.roulette = true;
+    factors.push_back(f);
+    return false;
+  };
   for (uint32_t bounce = 1; bounce <= max_depth; ++bounce) {
     HitRec rec;
     if (n_rays) (*n_rays)++;
@@ -1033,12 +1052,16 @@ double ray_reflectance(const HitCtx& c, Ray ray, const Rng& rng, uint32_t max_de
       V3 reflected = reflect(unit_vector(ray.d), rec.normal);
       V3 dir = reflected + mat.fuzz * random_in_unit_sphere(rng, bounce);
       factors.push_back(Factor{texture_value(s, mat.texture, ray, rec), 0, 0, false});
+      run = run * factors.back().atten;
       ray = Ray{rec.p, dir, ray.time, ray.wl};
+      if (roulette(bounce)) { cut = true; break; }
       continue;
     }
     if (mat.kind == YART_MAT_ISOTROPIC) { // material.rs:368-381
       factors.push_back(Factor{texture_value(s, mat.texture, ray, rec), 0, 0, false});
+      run = run * factors.back().atten;
       ray = Ray{rec.p, random_in_unit_sphere(rng, bounce), ray.time, ray.wl};
+      if (roulette(bounce)) { cut = true; break; }
       continue;
     }
     if (mat.kind == YART_MAT_DIELECTRIC) { // material.rs:213-301
@@ -1064,7 +1087,9 @@ double ray_reflectance(const HitCtx& c, Ray ray, const Rng& rng, uint32_t max_de
         dir = reflect(ray.d, rec.normal);
       }
       factors.push_back(Factor{1.0, 0, 0, false});
+      run = run * 1.0;
       ray = Ray{rec.p, dir, ray.time, ray.wl};
+      if (roulette(bounce)) { cut = true; break; }
       continue;
     }
     // Lambertian (material.rs:44-61) through the mixture pdf (main.rs:560-581)
@@ -1082,7 +1107,7 @@ double ray_reflectance(const HitCtx& c, Ray ray, const Rng& rng, uint32_t max_de
     };
     V3 dir;
     const bool have_lights = !s.lights.empty();
-    if (u_mix < 0.5) dir = have_lights ? lights_random(s, rec.p, u_pick, r1, r2) : cosine_dir();
+    if (u_mix < 0.5) dir = have_lights ? lights_random(s, rec.p, u_pick, r1, r2, (flags & YART_FLAG_UNBIASED_LIGHT_PICK) != 0) : cosine_dir();
     else dir = cosine_dir();
     Ray sc{rec.p, dir, ray.time, ray.wl};
     double cosv = dot(unit_vector(dir), uvw.w); // CosinePDF::value (pdf.rs:39-47)
@@ -1096,12 +1121,15 @@ double ray_reflectance(const HitCtx& c, Ray ray, const Rng& rng, uint32_t max_de
     double cs = dot(rec.normal, unit_vector(sc.d)); // Lambertian::scatter_pdf (material.rs:53-60)
     double spdf = cs < 0.0 ? 0.0 : cs / kPi;
     factors.push_back(Factor{atten, spdf, pdf_val, true});
+    run = run * atten * spdf / pdf_val;
     ray = sc;
+    if (roulette(bounce)) { cut = true; break; }
   }
-  double L = terminal;
+  double L = cut ? 0.0 : terminal;
   for (size_t i = factors.size(); i-- > 0;) {
     const Factor& f = factors[i];
-    if (f.diffuse) L = f.atten * L * f.spdf / f.pdf; // main.rs:578-581
+    if (f.roulette) L = L / f.atten;
+    else if (f.diffuse) L = f.atten * L * f.spdf / f.pdf; // main.rs:578-581
     else L = f.atten * L;                             // main.rs:553-554
   }
   return L;
@@ -1167,7 +1195,7 @@ void render_sample(const HitCtx& c, const Camera& cam, const yart_render_opts& o
                    std::vector<yart_ray>* dump) {
   Rng rng = make_rng(o.seed, py * o.width + px, sample);
   Ray r = camera_ray(cam, rng, px, py, o.width, o.height);
-  double refl = ray_reflectance(c, r, rng, o.max_depth, n_rays, scratch, dump);
+  double refl = ray_reflectance(c, r, rng, o.max_depth, n_rays, scratch, dump, o.flags);
   double cie[3];
   xyz_from_wavelength(r.wl, cie); // ray_color (main.rs:526-535)
   xyz[0] = cie[0] * refl; xyz[1] = cie[1] * refl; xyz[2] = cie[2] * refl;

@@ -62,3 +62,26 @@ def grid_tie_rays(h, n, seed=11):
     k = np.stack([g.integers(-2, 3, n), g.integers(-2, 3, n), g.integers(1, 4, n)], axis=1).astype(np.float64)
     v = np.stack([i, j, h[i, j]], axis=1).astype(np.float64)
     return v + 8.0 * k, -k
+
+
+def pixel_centre_rays(cam, width, height):
+    """One primary ray through the centre of every pixel, no lens, no jitter -- Camera::new / get_ray
+    (camera.rs:41-94) restated in numpy with s = (x + 0.5) / (W - 1), t = 1 - (y + 0.5) / (H - 1)
+    (the render loop's own mapping with the jitter at 0.5, main.rs:693-696).  `cam` is a yart_camera."""
+    lookfrom, lookat, vup = (np.array(list(v), dtype=np.float64) for v in (cam.lookfrom, cam.lookat, cam.vup))
+    theta = cam.vfov_degrees * np.pi / 180.0
+    vh = 2.0 * np.tan(theta / 2.0)
+    vw = cam.aspect_ratio * vh
+    w = lookfrom - lookat
+    w /= np.linalg.norm(w)
+    u = np.cross(vup, w)
+    u /= np.linalg.norm(u)
+    v = np.cross(w, u)
+    hor, ver = cam.focus_dist * vw * u, cam.focus_dist * vh * v
+    llc = lookfrom - hor / 2.0 - ver / 2.0 - cam.focus_dist * w
+    ys, xs = np.mgrid[0:height, 0:width]
+    s = ((xs + 0.5) / (width - 1)).reshape(-1, 1)
+    t = (1.0 - (ys + 0.5) / (height - 1)).reshape(-1, 1)
+    d = llc + s * hor + t * ver - lookfrom
+    o = np.broadcast_to(lookfrom, d.shape).copy()
+    return o, d

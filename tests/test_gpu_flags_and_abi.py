@@ -1,0 +1,311 @@
+"""GPU tests of the round-2 additions to the C ABI: sampling flags (vs the oracle's mirror), yart_closest_hit_f32,
+device-resident films + the NCCL communicator (yart_comm_*, yart_film_reduce), scene validation, memory-bounded
+batches."""
+import ctypes as C
+import os
+import subprocess
+import sys
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import raysets
+from test_gpu_render import compare_films
+
+pytestmark = pytest.mark.gpu
+INF = float("inf")
+ROOT = Path(__file__).resolve().parent.parent
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sampling flags
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scene,depth", [("cornell-box", 50), ("david", 50), ("cornell-box", 4)])
+def test_sampling_flags_match_the_oracle(yart, orc, ctx, scene, depth):
+    preset = yart.ScenePreset(scene, seed=1)
+    s = orc.Scene(preset)
+    ctx.set_scene(preset)
+    w = h = 64
+    cam = preset.camera(w, h)
+    base, st0 = ctx.render(cam, w, h, 0, 8, max_depth=depth, seed=3)
+    again, _ = ctx.render(cam, w, h, 0, 8, max_depth=depth, seed=3, flags=0)
+    assert np.array_equal(base, again)
+    combos = [yart.FLAG_UNBIASED_LIGHT_PICK, yart.FLAG_RUSSIAN_ROULETTE, yart.FLAG_DEPTH_ZERO_BLACK,
+              yart.FLAG_UNBIASED_LIGHT_PICK | yart.FLAG_RUSSIAN_ROULETTE | yart.FLAG_DEPTH_ZERO_BLACK]
+    for flags in combos:
+        want, st_w = s.render(cam, w, h, 0, 8, max_depth=depth, seed=3, n_threads=os.cpu_count(), flags=flags)
+        for order in (yart.ORDER_NEAR, yart.ORDER_REFERENCE):
+            got, st = ctx.render(cam, w, h, 0, 8, max_depth=depth, seed=3, order=order, flags=flags)
+            compare_films(got, want, "%s depth %d flags %d order %d" % (scene, depth, flags, order), 0.97)
+            assert abs(int(st.rays) - int(st_w.rays)) <= max(4, st_w.rays // 500)
+        if flags == yart.FLAG_RUSSIAN_ROULETTE and depth == 50:
+            assert st.rays < st0.rays
+        if flags == yart.FLAG_UNBIASED_LIGHT_PICK and scene == "cornell-box" and depth == 50:
+            assert got[..., 1].sum() < 0.85 * base[..., 1].sum()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# f32 ray records
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sycee", "david"])
+def test_closest_hit_f32_equals_the_f64_query_on_widened_rays(yart, orc, ctx, mesh_scene, name):
+    _, ms, s = mesh_scene(name)
+    ctx.set_scene(ms.desc)
+    info = s.qbvh_info(0)
+    o, d = raysets.uniform(300000, info.bbox_min, info.bbox_max, 31)
+    r32 = np.empty(len(o), dtype=yart.abi.RAY_F32_DTYPE)
+    r32["origin"], r32["direction"] = o.astype(np.float32), d.astype(np.float32)
+    r64 = orc.abi.make_rays(r32["origin"].astype(np.float64), r32["direction"].astype(np.float64))
+    want, _ = s.closest_hit(r64, 0, 0.001, INF, yart.ORDER_REFERENCE, n_threads=os.cpu_count())  # the ORACLE on the widened rays
+    for order in (yart.ORDER_REFERENCE, yart.ORDER_NEAR):
+        got, st = ctx.closest_hit_f32(r32, 0, 0.001, INF, order)
+        assert np.array_equal(got["prim_id"], want["prim_id"])
+        hit = want["prim_id"] != yart.MISS
+        assert np.array_equal(got["t"][hit], want["t"][hit].astype(np.float32))
+        assert np.array_equal(got["u"][hit], want["u"][hit].astype(np.float32))
+        assert np.array_equal(got["v"][hit], want["v"][hit].astype(np.float32))
+        assert np.isinf(got["t"][~hit]).all() and st.rays == len(r32)
+    # ragged sizes, the world target, and an unaligned-size tail
+    for n in (1, 33, 4099):
+        g, _ = ctx.closest_hit_f32(r32[:n], yart.TARGET_WORLD, 0.001, INF, yart.ORDER_NEAR)
+        assert np.array_equal(g["prim_id"], want["prim_id"][:n])
+    empty, st = ctx.closest_hit_f32(r32[:0], 0)
+    assert len(empty) == 0 and st.rays == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device films + communicator
+# ---------------------------------------------------------------------------------------------------------
+def test_device_film_round_trip_and_single_rank_comm(yart, ctx):
+    preset = yart.ScenePreset("cornell-box", seed=1)
+    ctx.set_scene(preset)
+    w = h = 64
+    cam = preset.camera(w, h)
+    want, _ = ctx.render(cam, w, h, 0, 6, seed=2)
+    film = ctx.film_create(w, h)
+    try:
+        assert not ctx.film_read(film, w, h).any()  # zeroed on creation
+        ctx.render_device(cam, w, h, 0, 6, film, seed=2)
+        assert np.array_equal(ctx.film_read(film, w, h), want)
+        comm = yart.Comm.from_id(ctx, yart.comm_unique_id(), 0, 1)  # a one-rank group: the reduce is the identity
+        info = comm.info()
+        assert info["n_ranks"] == 1 and info["n_local"] == 1 and info["nccl_version"] >= 20000
+        comm.film_reduce(film, w, h, root=0)
+        assert np.array_equal(ctx.film_read(film, w, h), want)
+        comm.film_reduce(film, w, h, root=-1)  # all-reduce flavour
+        assert np.array_equal(ctx.film_read(film, w, h), want)
+        with pytest.raises(yart.YartError):
+            comm.film_reduce(film, w, h, root=3)
+        comm.close()
+        ctx.film_clear(film, w, h)
+        assert not ctx.film_read(film, w, h).any()
+        # the same GPU twice is refused (one rank per GPU), loudly
+        with pytest.raises(yart.YartError):
+            yart.Comm.from_contexts([ctx, ctx])
+    finally:
+        ctx.film_destroy(film)
+
+
+def test_n_gpu_film_equals_one_gpu_film(yart):
+    """SURVEY.md 8(e) on hardware: N contexts in one process (one host thread each), every GPU renders its sample
+    range of every pixel, one in-place ncclReduce -- the root's film equals the 1-GPU film to f64-sum tolerance.
+    Needs >= 2 visible GPUs (`gpurun --gpus 2`); the one-rank path is covered by the test above."""
+    if yart.device_count() < 2:
+        pytest.skip("one GPU visible: the N-GPU equality needs `gpurun --gpus 2` (see profiles/r2_multi_gpu_film_equality.txt)")
+    sh = __import__("importlib").import_module("yet-another-raytracer_b200.sharding")
+    n = min(yart.device_count(), 4)
+    preset = yart.ScenePreset("david", seed=1)
+    w, h, spp = 320, 184, 37  # (37 does not divide evenly: ragged shards)
+    ctxs = [yart.Context(i) for i in range(n)]
+    for c in ctxs:
+        c.set_scene(preset)
+    cam = preset.camera(w, h)
+    single, st1 = ctxs[0].render(cam, w, h, 0, spp, seed=5)
+    films = [c.film_create(w, h) for c in ctxs]
+    comm = yart.Comm.from_contexts(ctxs)
+    assert comm.info()["n_ranks"] == n
+    errs = []
+
+    def work(r):
+        try:
+            lo, hi = sh.shard_range(0, spp, r, n)
+            ctxs[r].render_device(cam, w, h, lo, hi, films[r], seed=5)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(n)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+    comm.film_reduce(films, w, h, root=0)
+    got = ctxs[0].film_read(films[0], w, h)
+    err = np.abs(got - single).max() / np.abs(single).max()
+    print("N=%d GPUs: max |film_N - film_1| / max|film| = %.3g" % (n, err))
+    assert err <= 1e-13 and got.sum() > 0
+    other = ctxs[1].film_read(films[1], w, h)   # a non-root keeps its partial sum
+    assert other.sum() < got.sum()
+    comm.close()
+    for c, f in zip(ctxs, films):
+        c.film_destroy(f)
+        c.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# validation: a bad descriptor is YART_ERR_INVALID, never a wild device load
+# ---------------------------------------------------------------------------------------------------------
+def test_set_scene_rejects_malformed_descriptions(yart, ctx):
+    abi = yart.abi
+
+    def scene(objects, materials, textures, groups=(), images=()):
+        sd = abi.SceneDesc()
+        keep = []
+        for field, cls, items in (("objects", abi.Object, objects), ("materials", abi.Material, materials),
+                                  ("textures", abi.Texture, textures), ("groups", abi.Group, groups), ("images", abi.Image, images)):
+            arr = (cls * max(len(items), 1))(*items)
+            keep.append(arr)
+            setattr(sd, field, C.cast(arr, C.POINTER(cls)))
+            setattr(sd, "n_" + field, len(items))
+        return sd, keep
+
+    def sphere(material):
+        o = abi.Object()
+        o.kind, o.material, o.cos_theta = abi.OBJ_SPHERE, material, 1.0
+        o.p[3] = 1.0
+        return o
+
+    lam, tex = abi.Material(), abi.Texture()
+    lam.kind, tex.kind = abi.MAT_LAMBERTIAN, abi.TEX_SOLID
+    ok, keep = scene([sphere(0)], [lam], [tex])
+    ctx.set_scene(C.pointer(ok))
+    cases = {}
+    cases["object material out of range"] = scene([sphere(5)], [lam], [tex])
+    member = sphere(7)                                    # group member with a missing material
+    members = (abi.Object * 1)(member)
+    g = abi.Group()
+    g.members, g.n_members = C.cast(members, C.POINTER(abi.Object)), 1
+    grp = abi.Object()
+    grp.kind, grp.index, grp.cos_theta = abi.OBJ_GROUP, 0, 1.0
+    cases["group member material out of range"] = scene([grp], [lam], [tex], groups=[g])
+    img_tex = abi.Texture()
+    img_tex.kind, img_tex.image = abi.TEX_IMAGE, 0
+    pixels = (C.c_uint8 * 12)()
+    for wd, ht, ptr in ((0, 2, pixels), (2, 0, pixels), (2, 2, None)):   # empty images under a TEX_IMAGE
+        im = abi.Image()
+        im.width, im.height = wd, ht
+        im.rgb8 = C.cast(ptr, C.POINTER(C.c_uint8)) if ptr is not None else None
+        cases["image %dx%d %s" % (wd, ht, "null" if ptr is None else "data")] = scene([sphere(0)], [lam], [img_tex], images=[im])
+    bad_tex = abi.Material()
+    bad_tex.kind, bad_tex.texture = abi.MAT_LAMBERTIAN, 9
+    cases["material texture out of range"] = scene([sphere(0)], [bad_tex], [tex])
+    nullptr_objs, k2 = scene([sphere(0)], [lam], [tex])
+    nullptr_objs.objects = None                            # count 1, pointer null
+    cases["null objects pointer"] = (nullptr_objs, k2)
+    g2 = abi.Group()
+    g2.members, g2.n_members = None, 3
+    cases["null group members"] = scene([grp], [lam], [tex], groups=[g2])
+    for what, (sd, _keep) in cases.items():
+        with pytest.raises(yart.YartError) as e:
+            ctx.set_scene(C.pointer(sd))
+        assert e.value.code == -1, what
+        # and nothing half-built stays behind: a query now fails cleanly instead of touching freed tables
+        with pytest.raises(yart.YartError):
+            ctx.closest_hit(np.zeros(1, dtype=yart.RAY_DTYPE))
+    ctx.set_scene(C.pointer(ok))  # the context is still usable
+    hits, _ = ctx.closest_hit(yart.make_rays([(0, 0, -5)], [(0, 0, 1)]))
+    assert hits[0]["t"] == 4.0
+
+
+def test_stand_in_meshes_are_announced(yart, tmp_path):
+    for name in ("bunny", "teapot"):
+        p = yart.ScenePreset(name)
+        assert "stands in" in p.note and name + ".obj" in p.note
+    assert yart.ScenePreset("david").note == ""
+    code = ("import importlib, sys\nsys.path.insert(0, %r)\ny = importlib.import_module('yet-another-raytracer_b200')\n"
+            "try:\n    y.ScenePreset('bunny')\nexcept y.YartError as e:\n    print('code', e.code, e)\n") % str(ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, YART_STRICT_ASSETS="1"), capture_output=True, text=True)
+    assert "code -4" in out.stdout and "Failed to load OBJ file" in out.stdout, out.stdout + out.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------
+# memory-bounded batches
+# ---------------------------------------------------------------------------------------------------------
+def test_small_state_budget_gives_the_same_film(yart, ctx, tmp_path):
+    """The wavefront batch is sized from free device memory; forcing a 2 MB state budget (YART_TUNE_STATE_MB, read
+    once per process) cuts the frame into pixel chunks and sample batches -- the film must not change."""
+    preset = yart.ScenePreset("cornell-box", seed=1)
+    ctx.set_scene(preset)
+    w = h = 96
+    want, st = ctx.render(preset.camera(w, h), w, h, 0, 5, seed=6)
+    code = ("import importlib, sys, numpy as np\nsys.path.insert(0, %r)\n"
+            "y = importlib.import_module('yet-another-raytracer_b200')\np = y.ScenePreset('cornell-box', seed=1)\n"
+            "c = y.Context(0); c.set_scene(p)\nf, st = c.render(p.camera(96, 96), 96, 96, 0, 5, seed=6)\n"
+            "np.save(%r, f); print('launches', st.kernel_launches)\n") % (str(ROOT), str(tmp_path / "f.npy"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, YART_TUNE_STATE_MB="2"), capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert np.array_equal(np.load(tmp_path / "f.npy"), want)
+    assert int(out.stdout.split("launches")[1]) > st.kernel_launches  # it really ran in more, smaller batches
+
+
+def test_render_reports_nomem_instead_of_a_raw_cuda_error(yart, ctx):
+    """Hog the device (torch caching allocator) until less than the margin is free: yart_render must return
+    YART_ERR_NOMEM with a message, and work again once the memory is back."""
+    import torch
+    preset = yart.ScenePreset("cornell-box", seed=1)
+    ctx.set_scene(preset)
+    w = h = 64
+    cam = preset.camera(w, h)
+    c2 = yart.Context(0)  # a fresh context: it holds no state buffers yet, so only FREE memory counts for it
+    c2.set_scene(preset)
+    free, total = torch.cuda.mem_get_info(0)
+    hog = torch.empty(free - (96 << 20), dtype=torch.uint8, device="cuda:0")
+    try:
+        with pytest.raises(yart.YartError) as e:
+            c2.render(cam, w, h, 0, 1, seed=1)
+        assert e.value.code == -3 and "free device memory" in str(e.value)
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+    film, st = c2.render(cam, w, h, 0, 1, seed=1)
+    assert st.paths == w * h and film.sum() > 0
+    c2.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the renderer's own ray distribution
+# ---------------------------------------------------------------------------------------------------------
+def test_dump_path_rays_is_what_the_renderer_traces(yart, orc, ctx):
+    """yart_dump_path_rays: every world.hit ray of the paths, bounce by bounce.  Bounce 1 must be exactly the camera
+    rays (as a set: queue order is not pixel order), the count must equal the render's ray count, and tracing the dumped
+    rays -- a large set of REAL secondary rays, origins on surfaces -- must agree with the oracle bit for bit."""
+    preset = yart.ScenePreset("david", seed=1)
+    s = orc.Scene(preset)
+    ctx.set_scene(preset)
+    w, h, spp = 160, 96, 3
+    cam = preset.camera(w, h)
+    _, st = ctx.render(cam, w, h, 0, spp, seed=4)
+    rays, n = ctx.dump_path_rays(cam, w, h, 0, spp, 1 << 20, seed=4)
+    assert n == st.rays == len(rays)
+    prim, _, _ = orc.camera_rays(cam, w, h, 0, spp, seed=4)
+    key = lambda r: np.sort(np.ascontiguousarray(r).view([("", "<f8")] * 6).reshape(-1))  # noqa: E731
+    assert np.array_equal(key(rays[:w * h * spp]), key(prim))
+    # the oracle's own dump of the same samples: the same number of rays (up to a rare last-bit path flip), and most of
+    # them IDENTICAL bit for bit -- a bounce sampled through CUDA's sin / cos may differ from glibc's in the last bit of
+    # its direction, and every later ray of that path inherits the difference (measured: 87 % identical)
+    odump = s.dump_path_rays(cam, w, h, 0, spp, 1 << 20, seed=4)
+    assert abs(len(odump) - n) <= max(4, n // 1000)
+    common = np.intersect1d(key(rays), key(odump))
+    assert len(common) >= 0.7 * n
+    # capped output: the count is still the total
+    few, n2 = ctx.dump_path_rays(cam, w, h, 0, spp, 1000, seed=4)
+    assert n2 == n and len(few) == 1000 and np.array_equal(few, rays[:1000])
+    # batches of one sample: same rays, grouped sample by sample
+    by1, n3 = ctx.dump_path_rays(cam, w, h, 0, spp, 1 << 20, seed=4, batch_spp=1)
+    assert n3 == n and np.array_equal(key(by1), key(rays))
+    want, _ = s.closest_hit(rays, yart.TARGET_WORLD, 0.001, INF, yart.ORDER_REFERENCE, n_threads=os.cpu_count())
+    for order in (yart.ORDER_NEAR, yart.ORDER_REFERENCE):
+        got, _ = ctx.closest_hit(rays, yart.TARGET_WORLD, 0.001, INF, order)
+        for f in ("t", "u", "v", "prim_id", "obj_id", "front_face"):
+            assert np.array_equal(got[f], want[f]), f
+    assert (want["obj_id"] != yart.MISS).mean() > 0.4

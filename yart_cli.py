@@ -94,6 +94,8 @@ def main(argv=None):
     y = importlib.import_module("yet-another-raytracer_b200")
     args = build_parser(y.SCENE_NAMES).parse_args(argv)
     preset = y.ScenePreset(args.scene, seed=args.seed)
+    if preset.note:
+        print("note: " + preset.note, file=sys.stderr)
     o = preset.resolve_render_options(args.output, args.width, args.height, args.samples, args.max_depth,
                                       args.workers, args.vfov, args.aperture)
     start = time.time()  # the reference's timer starts in render(), after the scene is built (main.rs:591)
@@ -109,7 +111,9 @@ def main(argv=None):
             raise SystemExit("--resume needs --checkpoint FILE")
         if os.path.exists(args.checkpoint):
             film, done = load_checkpoint(args.checkpoint, ident)
-            done = min(done, total)
+            if done > total:  # the film already holds more samples than asked for: dividing it by `total` would over-expose
+                raise SystemExit("checkpoint %s already holds %d samples per pixel, more than --samples %d; "
+                                 "ask for at least that many" % (args.checkpoint, done, total))
             print("resuming %s at %d of %d samples per pixel" % (args.checkpoint, done, total))
     step = args.preview_every or total
     paths = rays = 0

@@ -18,8 +18,9 @@ from pathlib import Path
 import numpy as np
 
 from . import _abi as abi
-from ._abi import (FLAG_COUNT_VISITS, FLAG_DEVICE_PTRS, HIT_DTYPE, MISS, ORDER_NEAR, ORDER_REFERENCE, RAY_DTYPE,
-                   TARGET_WORLD, make_rays)
+from ._abi import (FLAG_COUNT_VISITS, FLAG_DEPTH_ZERO_BLACK, FLAG_DEVICE_PTRS, FLAG_RUSSIAN_ROULETTE,
+                   FLAG_UNBIASED_LIGHT_PICK, HIT_DTYPE, MISS, ORDER_NEAR, ORDER_REFERENCE, RAY_DTYPE, TARGET_WORLD,
+                   make_rays)
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
@@ -69,6 +70,7 @@ def load_library():
         "yart_measure_fetch_peak": (i32, [vp, u64, u32, u32, P(f64)]),
         "yart_preset_build": (i32, [C.c_char_p, C.c_char_p, u64, P(vp)]),
         "yart_preset_free": (None, [vp]),
+        "yart_preset_note": (C.c_char_p, [vp]),
         "yart_preset_scene": (P(abi.SceneDesc), [vp]),
         "yart_preset_get_info": (i32, [vp, P(abi.PresetInfo)]),
         "yart_preset_count": (i32, []),
@@ -83,9 +85,22 @@ def load_library():
         "yart_ctx_synchronize": (i32, [vp]),
         "yart_ctx_set_scene": (i32, [vp, P(abi.SceneDesc)]),
         "yart_closest_hit": (i32, [vp, u32, vp, u64, f64, f64, u32, u32, vp, P(abi.Stats)]),
+        "yart_closest_hit_f32": (i32, [vp, u32, vp, u64, C.c_float, C.c_float, u32, u32, vp, P(abi.Stats)]),
         "yart_render": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, P(abi.Stats)]),
         "yart_film_finalize": (i32, [vp, vp, u32, u32, u32, u32, vp]),
         "yart_generate_camera_rays": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, vp, vp]),
+        "yart_dump_path_rays": (i32, [vp, P(abi.Camera), P(abi.RenderOpts), vp, u64, P(u64)]),
+        "yart_comm_unique_id": (i32, [vp]),
+        "yart_comm_init_rank": (i32, [vp, vp, i32, i32, P(vp)]),
+        "yart_comm_init": (i32, [P(vp), i32, P(vp)]),
+        "yart_comm_destroy": (None, [vp]),
+        "yart_comm_info": (i32, [vp, P(i32), P(i32), P(i32), P(i32)]),
+        "yart_comm_last_error": (C.c_char_p, [vp]),
+        "yart_film_reduce": (i32, [vp, P(vp), u32, u32, i32]),
+        "yart_film_create": (i32, [vp, u32, u32, P(vp)]),
+        "yart_film_clear": (i32, [vp, vp, u32, u32]),
+        "yart_film_read": (i32, [vp, vp, u32, u32, vp]),
+        "yart_film_destroy": (None, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -102,7 +117,10 @@ EXPORTED_SYMBOLS = [
     "yart_resolve_dimensions", "yart_preset_camera", "yart_device_count", "yart_ctx_create", "yart_ctx_destroy",
     "yart_last_error", "yart_ctx_set_stream", "yart_ctx_synchronize", "yart_ctx_set_scene", "yart_closest_hit",
     "yart_render", "yart_film_finalize", "yart_generate_camera_rays", "yart_qbvh_shade", "yart_qbvh_build_device",
-    "yart_ctx_set_builder", "yart_measure_fetch_peak",
+    "yart_ctx_set_builder", "yart_measure_fetch_peak", "yart_comm_unique_id", "yart_comm_init_rank", "yart_comm_init",
+    "yart_comm_destroy", "yart_comm_info", "yart_comm_last_error", "yart_film_reduce", "yart_film_create",
+    "yart_film_clear", "yart_film_read", "yart_film_destroy", "yart_preset_note", "yart_closest_hit_f32",
+    "yart_dump_path_rays",
 ]
 
 
@@ -236,6 +254,7 @@ class ScenePreset:
         self.info = abi.PresetInfo()
         _check_global(_lib.yart_preset_get_info(self._h, C.byref(self.info)))
         self.desc = _lib.yart_preset_scene(self._h)  # POINTER(SceneDesc), borrowed
+        self.note = _lib.yart_preset_note(self._h).decode()  # "" or e.g. "bunny.obj is not shipped ...: sycee.obj stands in"
 
     def camera(self, width, height, vfov=None, aperture=None):
         cam = abi.Camera()
@@ -303,15 +322,37 @@ class Context:
         self._check(_lib.yart_ctx_synchronize(self._h))
 
     def closest_hit(self, rays, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"), order=ORDER_REFERENCE,
-                    count_visits=False):
-        """Batched `Hittable::hit` (reference hittable.rs:24) with host buffers."""
+                    count_visits=False, hits=None):
+        """Batched `Hittable::hit` (reference hittable.rs:24) with host buffers (`hits`: an optional preallocated --
+        e.g. pinned -- output array)."""
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
-        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        if hits is None:
+            hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        assert hits.dtype == HIT_DTYPE and hits.shape == (rays.shape[0],) and hits.flags.c_contiguous
         st = abi.Stats()
         flags = FLAG_COUNT_VISITS if count_visits else 0
         self._check(_lib.yart_closest_hit(self._h, target, rays.ctypes.data, rays.shape[0], t_min, t_max, order, flags,
                                           hits.ctypes.data, C.byref(st)))
         return hits, st
+
+    def closest_hit_f32(self, rays, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"), order=ORDER_REFERENCE,
+                        count_visits=False):
+        """yart_closest_hit_f32 with host buffers: rays is an array of abi.RAY_F32_DTYPE."""
+        rays = np.ascontiguousarray(rays, dtype=abi.RAY_F32_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=abi.HIT_F32_DTYPE)
+        st = abi.Stats()
+        flags = FLAG_COUNT_VISITS if count_visits else 0
+        self._check(_lib.yart_closest_hit_f32(self._h, target, rays.ctypes.data, rays.shape[0], t_min, t_max, order, flags,
+                                              hits.ctypes.data, C.byref(st)))
+        return hits, st
+
+    def closest_hit_f32_device(self, rays_ptr, n, hits_ptr, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"),
+                               order=ORDER_REFERENCE, count_visits=False):
+        st = abi.Stats()
+        flags = FLAG_DEVICE_PTRS | (FLAG_COUNT_VISITS if count_visits else 0)
+        self._check(_lib.yart_closest_hit_f32(self._h, target, C.c_void_p(rays_ptr), n, t_min, t_max, order, flags,
+                                              C.c_void_p(hits_ptr), C.byref(st)))
+        return st
 
     def closest_hit_device(self, rays_ptr, n, hits_ptr, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"),
                            order=ORDER_REFERENCE, count_visits=False):
@@ -330,7 +371,7 @@ class Context:
         return o
 
     def render(self, camera, width, height, sample_begin, sample_end, max_depth=50, seed=1, order=ORDER_NEAR,
-               batch_spp=0, film=None, count_visits=False):
+               batch_spp=0, film=None, count_visits=False, flags=0):
         """Batched sample loop of `render` (reference main.rs:650-708).  Returns (film, stats);
         film is the (H, W, 3) f64 sum of sanitised XYZ samples (continued if `film` is given;
         pass a pinned buffer for fast host<->device copies)."""
@@ -339,15 +380,15 @@ class Context:
         assert film.dtype == np.float64 and film.shape == (height, width, 3) and film.flags.c_contiguous
         st = abi.Stats()
         o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp,
-                       FLAG_COUNT_VISITS if count_visits else 0)
+                       (FLAG_COUNT_VISITS if count_visits else 0) | flags)
         self._check(_lib.yart_render(self._h, C.byref(camera), C.byref(o), film.ctypes.data, C.byref(st)))
         return film, st
 
     def render_device(self, camera, width, height, sample_begin, sample_end, film_ptr, max_depth=50, seed=1,
-                      order=ORDER_NEAR, batch_spp=0, count_visits=False):
+                      order=ORDER_NEAR, batch_spp=0, count_visits=False, flags=0):
         st = abi.Stats()
         o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, order, batch_spp,
-                       FLAG_DEVICE_PTRS | (FLAG_COUNT_VISITS if count_visits else 0))
+                       FLAG_DEVICE_PTRS | (FLAG_COUNT_VISITS if count_visits else 0) | flags)
         self._check(_lib.yart_render(self._h, C.byref(camera), C.byref(o), C.c_void_p(film_ptr), C.byref(st)))
         return st
 
@@ -359,6 +400,11 @@ class Context:
         self._check(_lib.yart_film_finalize(self._h, film.ctypes.data, w, h, spp, 0, rgba.ctypes.data))
         return rgba
 
+    def film_finalize_device(self, film_ptr, width, height, spp, rgba_ptr):
+        """Same with device pointers (film: [h][w][3] f64, rgba: [h][w][4] u8); asynchronous work is synchronised."""
+        self._check(_lib.yart_film_finalize(self._h, C.c_void_p(film_ptr), width, height, spp, FLAG_DEVICE_PTRS,
+                                            C.c_void_p(rgba_ptr)))
+
     def camera_rays(self, camera, width, height, sample_begin, sample_end, seed=1):
         n = width * height * (sample_end - sample_begin)
         rays = np.empty(n, dtype=RAY_DTYPE)
@@ -369,9 +415,126 @@ class Context:
                                                    wl.ctypes.data, tm.ctypes.data))
         return rays, wl, tm
 
+    def dump_path_rays(self, camera, width, height, sample_begin, sample_end, cap, max_depth=50, seed=1, batch_spp=0,
+                       out_ptr=None):
+        """Every ray the renderer traces for these samples, in wavefront order (yart_dump_path_rays).  Returns
+        (rays[:min(n, cap)], n) with host output, or n alone when out_ptr (a device pointer with room for cap) is given."""
+        n = C.c_uint64()
+        if out_ptr is not None:
+            o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, ORDER_NEAR, batch_spp, FLAG_DEVICE_PTRS)
+            self._check(_lib.yart_dump_path_rays(self._h, C.byref(camera), C.byref(o), C.c_void_p(out_ptr), cap, C.byref(n)))
+            return int(n.value)
+        rays = np.empty(cap, dtype=RAY_DTYPE)
+        o = self._opts(width, height, sample_begin, sample_end, max_depth, seed, ORDER_NEAR, batch_spp, 0)
+        self._check(_lib.yart_dump_path_rays(self._h, C.byref(camera), C.byref(o), rays.ctypes.data, cap, C.byref(n)))
+        return rays[:min(int(n.value), cap)], int(n.value)
+
+    # ---- device-resident films (what the multi-GPU reduce operates on) ----
+    def film_create(self, width, height):
+        """A zeroed [height][width][3] f64 film on this context's GPU; returns the device pointer (int)."""
+        p = C.c_void_p()
+        self._check(_lib.yart_film_create(self._h, width, height, C.byref(p)))
+        return p.value
+
+    def film_clear(self, film_ptr, width, height):
+        self._check(_lib.yart_film_clear(self._h, C.c_void_p(film_ptr), width, height))
+
+    def film_read(self, film_ptr, width, height, out=None):
+        if out is None:
+            out = np.empty((height, width, 3), dtype=np.float64)
+        assert out.dtype == np.float64 and out.shape == (height, width, 3) and out.flags.c_contiguous
+        self._check(_lib.yart_film_read(self._h, C.c_void_p(film_ptr), width, height, out.ctypes.data))
+        return out
+
+    def film_destroy(self, film_ptr):
+        if getattr(self, "_h", None) and _lib is not None and film_ptr:
+            _lib.yart_film_destroy(self._h, C.c_void_p(film_ptr))
+
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.yart_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+COMM_ID_BYTES = 128
+
+
+def _share_the_python_hosts_nccl():
+    """A Python host usually also carries PyTorch, whose libtorch_cuda needs ITS bundled libnccl.so.2 (the
+    nvidia-nccl wheel).  If our library bound the system's older copy first, a later `import torch` would fail on
+    missing symbols -- so point the library's run-time loader (YART_NCCL_LIB, csrc/device_comm.cu) at the wheel's
+    copy when there is one and the user has not chosen otherwise.  (The library itself first reuses any libnccl the
+    process has already loaded.)"""
+    if os.environ.get("YART_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = Path(base) / "lib" / "libnccl.so.2"
+            if cand.exists():
+                os.environ["YART_NCCL_LIB"] = str(cand)
+                return
+    except Exception:  # noqa: BLE001 -- no wheel: the system library is used
+        pass
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the C ABI: 128 bytes rank 0 ships to the other ranks (any transport)."""
+    _share_the_python_hosts_nccl()
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check_global(load_library().yart_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Comm:
+    """The multi-GPU group of the C ABI: sample-range sharding + one in-place NCCL reduce of the f64 film
+    (the replacement of the reference's tile gather, main.rs:746-760).
+
+    Comm.from_id(ctx, id, rank, n_ranks): one process per GPU;  Comm.from_contexts([ctx0, ctx1, ...]): one process."""
+
+    def __init__(self, handle, contexts):
+        self._h = handle
+        self.contexts = list(contexts)
+
+    @classmethod
+    def from_id(cls, ctx, unique_id, rank, n_ranks):
+        assert len(unique_id) == COMM_ID_BYTES
+        _share_the_python_hosts_nccl()
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        ctx._check(load_library().yart_comm_init_rank(ctx._h, buf, rank, n_ranks, C.byref(h)))
+        return cls(h, [ctx])
+
+    @classmethod
+    def from_contexts(cls, contexts):
+        _share_the_python_hosts_nccl()
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        h = C.c_void_p()
+        _check_global(load_library().yart_comm_init(arr, len(contexts), C.byref(h)))
+        return cls(h, contexts)
+
+    def info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check_global(_lib.yart_comm_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"n_ranks": a.value, "n_local": b.value, "first_local_rank": c.value, "nccl_version": d.value}
+
+    def film_reduce(self, film_ptrs, width, height, root=0):
+        """Sum the films onto `root` (root < 0: onto every rank), in place, asynchronous on each context's stream.
+        film_ptrs: one device pointer per local rank (an int is accepted for the one-rank-per-process case)."""
+        if isinstance(film_ptrs, int):
+            film_ptrs = [film_ptrs]
+        arr = (C.c_void_p * len(film_ptrs))(*film_ptrs)
+        rc = _lib.yart_film_reduce(self._h, arr, width, height, root)
+        if rc != 0:
+            raise YartError(rc, _lib.yart_comm_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.yart_comm_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -18,6 +18,7 @@ TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = range(4)
 NOISE_SQUARE, NOISE_TRILINEAR, NOISE_SMOOTH, NOISE_MARBLE, NOISE_NET = range(5)
 ORDER_REFERENCE, ORDER_NEAR = 0, 1
 FLAG_DEVICE_PTRS, FLAG_COUNT_VISITS = 1, 2
+FLAG_UNBIASED_LIGHT_PICK, FLAG_RUSSIAN_ROULETTE, FLAG_DEPTH_ZERO_BLACK = 4, 8, 16
 TARGET_WORLD = 0xFFFFFFFF
 MISS = 0xFFFFFFFF
 
@@ -107,6 +108,9 @@ RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("direction", "<f8", 3)])
 HIT_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim_id", "<u4"), ("obj_id", "<u4"),
                       ("front_face", "<u4"), ("_pad", "<u4")])
 assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 40
+RAY_F32_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3)])
+HIT_F32_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim_id", "<u4")])
+assert RAY_F32_DTYPE.itemsize == 24 and HIT_F32_DTYPE.itemsize == 16
 
 # the flat QBVH layout (csrc/host_common.h)
 NODE_DTYPE = np.dtype([("min_x", "<f4", 4), ("max_x", "<f4", 4), ("min_y", "<f4", 4), ("max_y", "<f4", 4),

@@ -10,6 +10,9 @@ Flags that matter:
   -Xcompiler -ffp-contract=off              same for the host-side QBVH build / camera maths
   -lineinfo                                 so ncu's source page maps SASS back to these files
 
+Every source is compiled to its own object (in parallel, cached under build/ by a digest of the source, the headers
+and the flags) and the objects are linked into the shared library; `build.log` keeps the ptxas -v output of all of them.
+
 --bounds-check builds a second library with -DYART_BOUNDS_CHECK: every index the kernels form (tree nodes,
 triangle records, traversal stack, ray / hit / queue slots) is checked and a violation traps.  It stands in
 for compute-sanitizer, which the GPU pool does not offer; run it with
@@ -19,6 +22,7 @@ import hashlib
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -26,29 +30,33 @@ CSRC = PKG / "csrc"
 ROOT = PKG.parent
 LIB = PKG / "libyart_b200.so"
 LIB_CHECKED = PKG / "libyart_b200_checked.so"
-STAMP = PKG / ".build_stamp"
+OBJ_DIR = PKG / "build"
 
-SOURCES = ["host_obj.cpp", "host_qbvh.cpp", "host_presets.cpp", "host_api.cpp", "yart_device.cu", "device_build.cu"]
+SOURCES = ["host_obj.cpp", "host_qbvh.cpp", "host_presets.cpp", "host_api.cpp", "yart_device.cu",
+           "device_build.cu", "device_comm.cu"]
 HEADERS = ["host_common.h", "device_common.cuh", "device_trace.cuh", "device_shade.cuh", "device_build.h"]
 INCLUDES = ["yart.h", "yart_rng.h", "yart_spectral_tables.h"]
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
     "-Xptxas", "-v",
-    "--shared", "-cudart", "shared",
 ]
-for knob in ("YART_TRAVERSE_MIN_BLOCKS", "YART_SHADE_MIN_BLOCKS", "YART_TRACE_THREADS", "YART_SHADE_THREADS"):  # tuning: resident blocks per SM compiled for
+LINK_FLAGS = ["--shared", "-cudart", "shared", "-ldl"]
+# tuning knobs: resident blocks per SM / CTA sizes the kernels are compiled for
+for knob in ("YART_TRAVERSE_MIN_BLOCKS", "YART_SHADE_MIN_BLOCKS", "YART_TRACE_THREADS", "YART_SHADE_THREADS"):
     if os.environ.get(knob):
-        NVCC_FLAGS += ["-D%s=%s" % (knob, os.environ[knob])]
+        COMPILE_FLAGS += ["-D%s=%s" % (knob, os.environ[knob])]
+for extra in os.environ.get("YART_NVCC_EXTRA", "").split():
+    COMPILE_FLAGS.append(extra)
 
 
-def _digest():
+def _digest(source, extra):
     h = hashlib.sha256()
-    for f in [CSRC / s for s in SOURCES + HEADERS] + [ROOT / "include" / i for i in INCLUDES] + [Path(__file__)]:
+    for f in [CSRC / source] + [CSRC / s for s in HEADERS] + [ROOT / "include" / i for i in INCLUDES] + [Path(__file__)]:
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(COMPILE_FLAGS + extra).encode())
     return h.hexdigest()
 
 
@@ -59,23 +67,49 @@ def nvcc_path():
     return "nvcc"
 
 
-def build(force=False, verbose=False, bounds_check=False):
-    digest = _digest()
-    lib = LIB_CHECKED if bounds_check else LIB
-    stamp = PKG / (".build_stamp_checked" if bounds_check else ".build_stamp")
-    if not force and lib.exists() and stamp.exists() and stamp.read_text().strip() == digest:
-        return str(lib)
-    extra = ["-DYART_BOUNDS_CHECK"] if bounds_check else []
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", str(lib)] + [str(CSRC / s) for s in SOURCES]
+def _compile(source, extra, tag, force):
+    obj = OBJ_DIR / ("%s%s.o" % (source.replace(".", "_"), tag))
+    stamp = obj.with_suffix(".digest")
+    log = obj.with_suffix(".log")
+    digest = _digest(source, extra)
+    if not force and obj.exists() and stamp.exists() and log.exists() and stamp.read_text().strip() == digest:
+        return obj, log.read_text(), 0
+    cmd = [nvcc_path()] + COMPILE_FLAGS + extra + ["-c", str(CSRC / source), "-o", str(obj)]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    (PKG / ("build_checked.log" if bounds_check else "build.log")).write_text(" ".join(cmd) + "\n" + log)
+    text = " ".join(cmd) + "\n" + res.stdout + res.stderr
+    log.write_text(text)
+    if res.returncode == 0:
+        stamp.write_text(digest)
+    return obj, text, res.returncode
+
+
+def build(force=False, verbose=False, bounds_check=False):
+    lib = LIB_CHECKED if bounds_check else LIB
+    tag = "_checked" if bounds_check else ""
+    extra = ["-DYART_BOUNDS_CHECK"] if bounds_check else []
+    OBJ_DIR.mkdir(exist_ok=True)
+    lib_stamp = PKG / (".build_stamp_checked" if bounds_check else ".build_stamp")
+    total = hashlib.sha256("".join(_digest(s, extra) for s in SOURCES).encode()).hexdigest()
+    if not force and lib.exists() and lib_stamp.exists() and lib_stamp.read_text().strip() == total:
+        return str(lib)
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda s: _compile(s, extra, tag, force), SOURCES))
+    logs = "".join(r[1] for r in results)
+    log_path = PKG / ("build_checked.log" if bounds_check else "build.log")
+    if any(r[2] for r in results):
+        log_path.write_text(logs)
+        sys.stderr.write("".join(r[1] for r in results if r[2]))
+        raise RuntimeError("nvcc failed (see %s)" % log_path)
+    cmd = [nvcc_path()] + LINK_FLAGS + ["-o", str(lib)] + [str(r[0]) for r in results]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    logs += " ".join(cmd) + "\n" + res.stdout + res.stderr
+    log_path.write_text(logs)
     if res.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed (see %s)" % (PKG / "build.log"))
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("link failed (see %s)" % log_path)
     if verbose:
-        print(log)
-    stamp.write_text(digest)
+        print(logs)
+    lib_stamp.write_text(total)
     return str(lib)
 
 

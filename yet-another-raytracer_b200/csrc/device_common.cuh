@@ -185,6 +185,27 @@ YART_DEV void store_ray(yart_ray* p, D3 o, D3 d) {
   q[2] = make_double2(d.y, d.z);
 }
 
+// f32 ray records (yart_ray_f32, 24 bytes, 8-byte aligned): widened exactly; three 64-bit accesses
+YART_DEV void load_ray_f32(const yart_ray_f32* p, D3& o, D3& d) {
+  const float2* q = reinterpret_cast<const float2*>(p);
+  const float2 a = q[0], b = q[1], c = q[2];
+  o = d3((double)a.x, (double)a.y, (double)b.x);
+  d = d3((double)b.y, (double)c.x, (double)c.y);
+}
+
+// A finished path's sample value (XYZ before sanitising) lives in the first 24 bytes of its ray record.
+YART_DEV void store_sample(yart_ray* p, double x, double y, double z) {
+  double2* q = reinterpret_cast<double2*>(p);
+  q[0] = make_double2(x, y);
+  reinterpret_cast<double*>(p)[2] = z;
+}
+YART_DEV void load_sample(const yart_ray* p, double& x, double& y, double& z) {
+  const double2 a = reinterpret_cast<const double2*>(p)[0];
+  x = a.x;
+  y = a.y;
+  z = reinterpret_cast<const double*>(p)[2];
+}
+
 // What a closest-hit query leaves behind for the shade stage (32 bytes).
 struct alignas(16) DevHit {
   double t;      // +inf on a miss

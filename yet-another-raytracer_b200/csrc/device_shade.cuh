@@ -378,12 +378,15 @@ YART_DEV double lights_pdf_value(const DevScene& S, D3 origin, D3 direction) { /
   for (uint32_t i = 0; i < S.n_lights; ++i) sum += weight * light_pdf_value(S.lights[i], origin, direction);
   return sum;
 }
-YART_DEV D3 lights_random(const DevScene& S, D3 origin, double u_pick, double r1, double r2) { // hittable.rs:113-122
+// hittable.rs:113-122: `gen_range(0..len-1)` never picks the last light although pdf_value averages over all of
+// them.  unbiased (YART_FLAG_UNBIASED_LIGHT_PICK): uniform over all n lights.
+YART_DEV D3 lights_random(const DevScene& S, D3 origin, double u_pick, double r1, double r2, bool unbiased) {
   const uint32_t n = S.n_lights;
   if (n == 0) return d3(1.0, 0.0, 0.0);
   if (n == 1) return light_random(S.lights[0], origin, r1, r2);
-  uint32_t k = (uint32_t)(u_pick * (double)(n - 1));
-  if (k > n - 2) k = n - 2;
+  const uint32_t m = unbiased ? n : n - 1;
+  uint32_t k = (uint32_t)(u_pick * (double)m);
+  if (k > m - 1) k = m - 1;
   return light_random(S.lights[k], origin, r1, r2);
 }
 
@@ -425,7 +428,8 @@ struct PathState { // SoA over the paths of one batch, indexed by path id = pixe
   double* wavelength;
   double* throughput;
   DevHit* hits;
-  double* contrib; // [n][3]: the sample's XYZ before sanitising, written once when the path ends
+  // The sample's XYZ (before sanitising) is written once, when the path ends, into the first 24 bytes of the
+  // path's own -- by then dead -- ray record: k_film_accumulate reads it from there.
 };
 
 struct RenderParams {
@@ -439,7 +443,7 @@ struct RenderParams {
   // objects [tail_begin, tail_end) of the world list -- a trailing run of plain spheres -- are intersected by
   // k_shade itself (it has the ray and the hit in hand) instead of costing a pass over the queue
   uint32_t tail_begin, tail_end;
-  uint32_t _pad;
+  uint32_t flags; // YART_FLAG_UNBIASED_LIGHT_PICK | RUSSIAN_ROULETTE | DEPTH_ZERO_BLACK (all off = the reference)
   uint64_t seed;
 };
 
@@ -504,9 +508,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams R, uint32_t* 
         R.st.throughput[id] = 1.0;
         alive = true;
       } else { // outside the reference's 8x8 tiles (main.rs:643-646): never sampled
-        R.st.contrib[id * 3 + 0] = 0.0;
-        R.st.contrib[id * 3 + 1] = 0.0;
-        R.st.contrib[id * 3 + 2] = 0.0;
+        store_sample(R.st.rays + id, 0.0, 0.0, 0.0);
       }
     }
     const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
@@ -616,7 +618,7 @@ YART_DEV bool shade_path(const RenderParams& R, uint32_t id, uint32_t bounce) {
       const bool have_lights = S.n_lights != 0;
       D3 dir;
       if (u_mix < 0.5 && have_lights) {
-        dir = lights_random(S, rec.p, u_pick, r1, r2);
+        dir = lights_random(S, rec.p, u_pick, r1, r2, (R.flags & YART_FLAG_UNBIASED_LIGHT_PICK) != 0);
       } else { // random_cosine_direction (pdf.rs:15-25)
         const double z = sqrt(1.0 - r2);
         const double phi = 2.0 * kPi * r1;
@@ -640,17 +642,27 @@ YART_DEV bool shade_path(const RenderParams& R, uint32_t id, uint32_t bounce) {
       }
     }
   }
-  if (!done && bounce >= R.max_depth) { // depth exhausted: ray_reflectance(depth 0) = 1.0
+  if (!done && (R.flags & YART_FLAG_RUSSIAN_ROULETTE) && bounce >= YART_RR_FIRST_BOUNCE) {
+    // Russian roulette (off in the reference): survive with probability q = clamp(throughput, 0.05, 1), unbiased
+    const double q = thr < YART_RR_MIN_SURVIVAL ? YART_RR_MIN_SURVIVAL : (thr > 1.0 ? 1.0 : thr);
+    double u_rr, unused;
+    rng_draw(rng, bounce, YART_SLOT_RR, u_rr, unused);
+    if (u_rr >= q) {
+      done = true;
+      terminal = 0.0;
+    } else {
+      thr = thr / q;
+    }
+  }
+  if (!done && bounce >= R.max_depth) { // depth exhausted: ray_reflectance(depth 0) = 1.0 (main.rs:544-546)
     done = true;
-    terminal = 1.0;
+    terminal = (R.flags & YART_FLAG_DEPTH_ZERO_BLACK) ? 0.0 : 1.0;
   }
   if (done) {
     const double refl = thr * terminal;
     double cie[3];
     xyz_from_wavelength(S, wl, cie);
-    R.st.contrib[(size_t)id * 3 + 0] = cie[0] * refl;
-    R.st.contrib[(size_t)id * 3 + 1] = cie[1] * refl;
-    R.st.contrib[(size_t)id * 3 + 2] = cie[2] * refl;
+    store_sample(R.st.rays + id, cie[0] * refl, cie[1] * refl, cie[2] * refl);
   } else {
     store_ray(R.st.rays + id, next_o, next_d);
     R.st.throughput[id] = thr;
@@ -706,7 +718,11 @@ __global__ void __launch_bounds__(kShadeThreads, YART_SHADE_MIN_BLOCKS) k_shade(
         YART_CHECK(obj == YART_MISS || obj < S.n_objects);
         cls = 0;
         if (obj != YART_MISS) {
-          const uint32_t kind = S.materials[S.objects[obj].material].kind;
+          const yart_object& ob = S.objects[obj];
+          uint32_t mi = ob.material;
+          if (ob.kind == YART_OBJ_GROUP && !(ob.wrap & YART_WRAP_MEDIUM)) // a group is shaded with its member's material
+            mi = S.groups[ob.index].members[R.st.hits[my_id].prim >> 3].material;
+          const uint32_t kind = S.materials[mi].kind;
           cls = (kind == YART_MAT_LAMBERTIAN) ? 1u : ((kind == YART_MAT_DIELECTRIC) ? 2u
                 : ((kind == YART_MAT_NONE || kind == YART_MAT_DIFFUSE_LIGHT) ? 0u : 3u));
         }
@@ -754,9 +770,10 @@ __global__ void __launch_bounds__(256) k_film_accumulate(const RenderParams R, d
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < R.n_pixels; p += gridDim.x * blockDim.x) {
     double* px = film + (size_t)(R.pixel_base + p) * 3;
     double ax = px[0], ay = px[1], az = px[2];
-    const double* c = R.st.contrib + (size_t)p * R.spp_batch * 3;
+    const yart_ray* c = R.st.rays + (size_t)p * R.spp_batch;
     for (uint32_t s = 0; s < R.spp_batch; ++s) {
-      double x = c[s * 3 + 0], y = c[s * 3 + 1], z = c[s * 3 + 2];
+      double x, y, z;
+      load_sample(c + s, x, y, z);
       if (!isfinite(x) || !isfinite(y) || !isfinite(z)) {
         x = y = z = 0.0;
       } else if (!(y <= 0.0 || y <= 20.0)) {

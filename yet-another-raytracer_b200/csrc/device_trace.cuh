@@ -264,6 +264,7 @@ YART_DEV bool object_hit_t(const DevScene& S, const yart_object& o, uint32_t obj
 // ---------------------------------------------------------------------------------------------
 struct PassCommon {
   const yart_ray* rays;        // indexed by ray id
+  const yart_ray_f32* rays32;  // non-null: the rays are f32 records instead (yart_closest_hit_f32), `rays` is unused
   const uint32_t* queue;       // work item -> ray id, null = identity
   const uint32_t* n_items_dev; // number of work items in device memory, null = use n_items
   uint64_t n_items;
@@ -428,9 +429,15 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
       if (nxt_stage == 2) {
         if (id_nxt != YART_MISS) {
           YART_CHECK(id_nxt < P.c.n_rays);
-          const char* rp = reinterpret_cast<const char*>(P.c.rays + id_nxt);
-          prefetch_l2(rp);
-          prefetch_l2(rp + 32); // a 48-byte record always spans two 32-byte sectors
+          if (P.c.rays32) {
+            const char* rp = reinterpret_cast<const char*>(P.c.rays32 + id_nxt);
+            prefetch_l2(rp);
+            prefetch_l2(rp + 23); // a 24-byte record may straddle two 32-byte sectors
+          } else {
+            const char* rp = reinterpret_cast<const char*>(P.c.rays + id_nxt);
+            prefetch_l2(rp);
+            prefetch_l2(rp + 32); // a 48-byte record always spans two 32-byte sectors
+          }
           if (!P.c.first_pass) prefetch_l2(P.c.hits + id_nxt);
         }
         nxt_stage = 3;
@@ -488,7 +495,8 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           ray_id = new_id;
           YART_CHECK(ray_id < P.c.n_rays);
           D3 ro, rd;
-          load_ray(P.c.rays + ray_id, ro, rd);
+          if (P.c.rays32) load_ray_f32(P.c.rays32 + ray_id, ro, rd);
+          else load_ray(P.c.rays + ray_id, ro, rd);
           t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
           // ray into the instance's space (hittable.rs:137-143, 218-227); uniform across the launch
           if (P.wrap & YART_WRAP_TRANSLATE) ro = ro - d3(P.offset[0], P.offset[1], P.offset[2]);
@@ -736,7 +744,8 @@ __global__ void __launch_bounds__(256) k_analytic(const AnalyticParams P) {
     const uint32_t ray_id = P.c.queue ? P.c.queue[item] : (uint32_t)item;
     YART_CHECK(ray_id < P.c.n_rays);
     D3 wo, wd;
-    load_ray(P.c.rays + ray_id, wo, wd);
+    if (P.c.rays32) load_ray_f32(P.c.rays32 + ray_id, wo, wd);
+    else load_ray(P.c.rays + ray_id, wo, wd);
     DevHit h;
     if (P.c.first_pass) {
       h.t = d_inf(); h.bu = 0.0; h.bv = 0.0; h.obj = YART_MISS; h.prim = 0;

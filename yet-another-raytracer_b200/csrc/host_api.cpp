@@ -2,6 +2,7 @@
 // scene presets, option resolution.  No CUDA in this file.
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <new>
 
 #include "host_common.h"
@@ -13,9 +14,26 @@ struct yart_preset {
   yart::Preset p;
 };
 
+// extern "C" bodies must not let C++ exceptions cross the ABI (a std::bad_alloc while loading a large OBJ, ...)
+#define YART_HOST_GUARD_BEGIN try {
+#define YART_HOST_GUARD_END(fn_name)                                                          \
+  }                                                                                           \
+  catch (const std::bad_alloc&) {                                                             \
+    yart::set_global_error(std::string(fn_name) + ": out of host memory");                    \
+    return YART_ERR_NOMEM;                                                                    \
+  }                                                                                           \
+  catch (const std::exception& e) {                                                           \
+    yart::set_global_error(std::string(fn_name) + ": " + e.what());                           \
+    return YART_ERR_INVALID;                                                                  \
+  }                                                                                           \
+  catch (...) {                                                                               \
+    yart::set_global_error(std::string(fn_name) + ": unknown C++ exception");                 \
+    return YART_ERR_INVALID;                                                                  \
+  }
+
 extern "C" {
 
-const char* yart_version(void) { return "yart-b200 0.1 (abi 1)"; }
+const char* yart_version(void) { return "yart-b200 0.2 (abi 2)"; }
 const char* yart_last_error_global(void) { return yart::global_error().c_str(); }
 
 int yart_obj_load(const char* path, yart_objfile** out) {
@@ -25,14 +43,20 @@ int yart_obj_load(const char* path, yart_objfile** out) {
   }
   yart_objfile* o = new (std::nothrow) yart_objfile();
   if (!o) return YART_ERR_NOMEM;
+  struct Drop {
+    yart_objfile* p;
+    ~Drop() { delete p; }
+  } drop{o};
+  YART_HOST_GUARD_BEGIN
   std::string err;
   if (!yart::load_obj(path, o->soup, err)) {
-    delete o;
     yart::set_global_error(err);
     return YART_ERR_IO;
   }
+  drop.p = nullptr;
   *out = o;
   return YART_OK;
+  YART_HOST_GUARD_END("yart_obj_load")
 }
 void yart_obj_free(yart_objfile* obj) { delete obj; }
 int yart_obj_trimesh(const yart_objfile* obj, yart_trimesh* out) {
@@ -51,15 +75,21 @@ int yart_qbvh_build(const yart_trimesh* mesh, yart_qbvh** out) {
   }
   yart_qbvh* q = new (std::nothrow) yart_qbvh();
   if (!q) return YART_ERR_NOMEM;
+  struct Drop {
+    yart_qbvh* p;
+    ~Drop() { delete p; }
+  } drop{q};
+  YART_HOST_GUARD_BEGIN
   std::string err;
   if (!yart::build_qbvh(*mesh, q->q, err)) {
-    delete q;
     yart::set_global_error(err);
     return YART_ERR_INVALID;
   }
   q->n_tris = mesh->n_tris;
+  drop.p = nullptr;
   *out = q;
   return YART_OK;
+  YART_HOST_GUARD_END("yart_qbvh_build")
 }
 void yart_qbvh_free(yart_qbvh* q) { delete q; }
 int yart_qbvh_get_info(const yart_qbvh* q, yart_qbvh_info* out) {
@@ -91,16 +121,23 @@ int yart_preset_build(const char* name, const char* assets_dir, uint64_t seed, y
   }
   yart_preset* p = new (std::nothrow) yart_preset();
   if (!p) return YART_ERR_NOMEM;
+  struct Drop {
+    yart_preset* p;
+    ~Drop() { delete p; }
+  } drop{p};
+  YART_HOST_GUARD_BEGIN
   std::string err;
   if (!yart::build_preset(name, assets_dir, seed, p->p, err)) {
-    delete p;
     yart::set_global_error(err);
     return err.rfind("unknown scene", 0) == 0 ? YART_ERR_INVALID : YART_ERR_IO;
   }
+  drop.p = nullptr;
   *out = p;
   return YART_OK;
+  YART_HOST_GUARD_END("yart_preset_build")
 }
 void yart_preset_free(yart_preset* p) { delete p; }
+const char* yart_preset_note(const yart_preset* p) { return p ? p->p.note.c_str() : ""; }
 const yart_scene_desc* yart_preset_scene(const yart_preset* p) { return p ? &p->p.scene.desc : nullptr; }
 int yart_preset_get_info(const yart_preset* p, yart_preset_info* out) {
   if (!p || !out) {

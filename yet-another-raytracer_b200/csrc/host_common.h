@@ -99,6 +99,7 @@ struct OwnedScene {
 struct Preset {
   OwnedScene scene;
   yart_preset_info info;
+  std::string note; // deviations a user must be told about (a stand-in mesh for a missing OBJ file); empty otherwise
 };
 bool build_preset(const std::string& name, const std::string& assets_dir, uint64_t seed, Preset& out,
                   std::string& err);

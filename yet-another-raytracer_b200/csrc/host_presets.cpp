@@ -12,6 +12,7 @@
 //   * bunny / teapot: bunny.obj and teapot.obj are not shipped; sycee.obj stands in.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/yart_rng.h"
@@ -193,6 +194,24 @@ struct B { // scene builder helpers
     if (!load_obj(path, s.soups.back(), err)) return false;
     index = (uint32_t)s.soups.size() - 1;
     return true;
+  }
+  // bunny.obj / teapot.obj are not shipped with the reference (its .MISSING_LARGE_BLOBS lists them; the Rust binary
+  // stops with "Failed to load OBJ file", triangle.rs:112-113).  Use the real file when the caller's assets directory
+  // has it; otherwise sycee.obj stands in -- and the preset SAYS so (yart_preset_note), or, with YART_STRICT_ASSETS=1
+  // in the environment, fails like the reference.
+  bool load_mesh_or_stand_in(const std::string& assets, const char* wanted, uint32_t& index, std::string& note, std::string& err) {
+    const std::string real = assets + "/" + wanted;
+    if (FILE* f = fopen(real.c_str(), "rb")) {
+      fclose(f);
+      return load_mesh(real, index, err);
+    }
+    const char* strict = getenv("YART_STRICT_ASSETS");
+    if (strict && *strict && *strict != '0') {
+      err = "Failed to load OBJ file '" + real + "' (not shipped with the reference; YART_STRICT_ASSETS forbids the sycee.obj stand-in)";
+      return false;
+    }
+    note = std::string("input/") + wanted + " is not shipped with the reference (.MISSING_LARGE_BLOBS): sycee.obj stands in for it";
+    return load_mesh(assets + "/sycee.obj", index, err);
   }
   bool load_earth(const std::string& assets, uint32_t& image, std::string& err) { // ImageTexture::new("input/earthmap.jpg")
     const std::string path = assets + "/earthmap_1024x512.rgb8";
@@ -420,7 +439,7 @@ bool build_preset(const std::string& name, const std::string& assets, uint64_t s
     b.add(B::sphere(30.0, 40.0, -30.0, 20.0, light));
     b.add(B::sphere(-20.0, 10.0, 50.0, 10.0, light));
     uint32_t m;
-    if (!b.load_mesh(assets + "/sycee.obj", m, err)) return false;
+    if (!b.load_mesh_or_stand_in(assets, "teapot.obj", m, out.note, err)) return false;
     b.add(B::mesh(m, glass));
     b.ground_quad(80.0, 120.0, ground);
     uint32_t none = b.no_material();
@@ -431,7 +450,7 @@ bool build_preset(const std::string& name, const std::string& assets, uint64_t s
   } else if (name == "bunny") { // scenes.rs:535-579, main.rs:333-349 (bunny.obj missing -> sycee.obj)
     uint32_t glass = b.sf66(), ground = b.lambertian(0.5, 0.5, 0.5), light = b.diffuse_light(5.0, 5.0, 5.0);
     uint32_t m;
-    if (!b.load_mesh(assets + "/sycee.obj", m, err)) return false;
+    if (!b.load_mesh_or_stand_in(assets, "bunny.obj", m, out.note, err)) return false;
     b.add(B::mesh(m, glass));
     b.ground_quad(20.0, 30.0, ground);
     b.add(B::sphere(0.0, 6.0, -2.0, 2.0, light)); // emitter at z=-2, sampling light at z=+2 (A-11)

@@ -57,6 +57,42 @@ __global__ void __launch_bounds__(256) k_export(const DevScene S, const yart_ray
   }
 }
 
+// yart_closest_hit_f32: DevHit -> yart_hit_f32 (values rounded to nearest f32; original triangle id as k_export)
+__global__ void __launch_bounds__(256) k_export_f32(const DevScene S, const yart_object* objects, const DevHit* hits, yart_hit_f32* out_hits,
+                                                     uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const DevHit h = hits[i];
+    yart_hit_f32 out;
+    if (h.obj == YART_MISS) {
+      out.t = __int_as_float(0x7f800000); out.u = 0.f; out.v = 0.f; out.prim_id = YART_MISS;
+    } else {
+      const yart_object& o = objects[h.obj];
+      out.t = (float)h.t; out.u = (float)h.bu; out.v = (float)h.bv;
+      if (o.wrap & YART_WRAP_MEDIUM) out.prim_id = 0;
+      else if (o.kind == YART_OBJ_MESH) out.prim_id = __float_as_uint(__ldg(S.meshes[o.index].tris + (size_t)h.prim * 3).w);
+      else if (o.kind == YART_OBJ_GROUP) out.prim_id = S.groups[o.index].member_orig[h.prim >> 3];
+      else out.prim_id = h.prim;
+    }
+    out_hits[i] = out;
+  }
+}
+
+// yart_dump_path_rays: the rays of bounce b (queue order) appended to `out` behind those of the earlier bounces of the
+// batch (their counts are counts[1 .. b-1]) and of the earlier batches (`base`)
+__global__ void __launch_bounds__(256) k_dump_rays(const yart_ray* __restrict__ rays, const uint32_t* __restrict__ queue,
+                                                    const uint32_t* __restrict__ counts, uint32_t b, uint64_t base,
+                                                    yart_ray* __restrict__ out, uint64_t cap) {
+  uint64_t off = base;
+  for (uint32_t j = 1; j < b; ++j) off += counts[j];
+  const uint32_t n = counts[b];
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (off + i >= cap) break;
+    D3 o, d;
+    load_ray(rays + queue[i], o, d);
+    store_ray(out + off + i, o, d);
+  }
+}
+
 // DevMesh::leafgeo from the flattened tree: one thread per (node, child); a leaf child's triangles are copied
 // vertex by vertex (9 floats each) to 64 B x (position of its first triangle)
 __global__ void __launch_bounds__(256) k_pack_leaves(const FlatNode* __restrict__ nodes, uint32_t n_nodes, const FlatTri* __restrict__ tris,
@@ -101,9 +137,30 @@ namespace {
     cudaError_t e__ = (expr);                                                                \
     if (e__ != cudaSuccess) {                                                                \
       (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+      if (e__ == cudaErrorMemoryAllocation) {                                                \
+        cudaGetLastError(); /* not sticky: clear it so that the context stays usable */      \
+        return YART_ERR_NOMEM;                                                               \
+      }                                                                                      \
       return YART_ERR_CUDA;                                                                  \
     }                                                                                        \
   } while (0)
+
+// extern "C" bodies must not let C++ exceptions cross the ABI (std::bad_alloc from a vector, ...)
+#define YART_ABI_GUARD_BEGIN try {
+#define YART_ABI_GUARD_END(ctx, fn_name)                                                       \
+  }                                                                                          \
+  catch (const std::bad_alloc&) {                                                            \
+    if (ctx) (ctx)->err = std::string(fn_name) + ": out of host memory";                        \
+    return YART_ERR_NOMEM;                                                                   \
+  }                                                                                          \
+  catch (const std::exception& e) {                                                          \
+    if (ctx) (ctx)->err = std::string(fn_name) + ": " + e.what();                               \
+    return YART_ERR_INVALID;                                                                 \
+  }                                                                                          \
+  catch (...) {                                                                              \
+    if (ctx) (ctx)->err = std::string(fn_name) + ": unknown C++ exception";                     \
+    return YART_ERR_INVALID;                                                                 \
+  }
 
 int tune_env(const char* name, int dflt) { // tuning / debugging knobs from the environment
   const char* v = getenv(name);
@@ -115,7 +172,7 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFree(p); // (cudaFree synchronises the device: work still using the old buffer has finished)
     p = nullptr;
     cap = 0;
     cudaError_t e = cudaMalloc(&p, bytes);
@@ -270,8 +327,7 @@ struct yart_ctx {
   double* d_smits = nullptr;
 
   // work buffers
-  DevBuf rays, hits_export, time, wavelength, throughput, hits, contrib, queue_a, queue_b, counts, work, counters, film,
-      rgba;
+  DevBuf rays, hits_export, time, wavelength, throughput, hits, queue_a, queue_b, counts, work, counters, film, rgba;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;
 
@@ -282,6 +338,12 @@ struct yart_ctx {
     d_solo = nullptr;
   }
 };
+
+namespace yart { // accessors for the other translation units of the library (device_comm.cu)
+cudaStream_t ctx_stream(yart_ctx* ctx) { return ctx->stream; }
+int ctx_device(const yart_ctx* ctx) { return ctx->device; }
+void ctx_set_error(yart_ctx* ctx, const std::string& msg) { ctx->err = msg; }
+} // namespace yart
 
 namespace {
 
@@ -500,10 +562,14 @@ int yart_ctx_create(int device, yart_ctx** out) {
     delete ctx;
     return YART_ERR_CUDA;
   }
-  cudaMemcpy(ctx->d_cie, YART_CIE_X, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice);
-  cudaMemcpy(ctx->d_cie + YART_N_CIE, YART_CIE_Y, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice);
-  cudaMemcpy(ctx->d_cie + 2 * YART_N_CIE, YART_CIE_Z, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice);
-  cudaMemcpy(ctx->d_smits, YART_SMITS_BASIS, sizeof(double) * 7 * YART_N_BINS, cudaMemcpyHostToDevice);
+  if ((e = cudaMemcpy(ctx->d_cie, YART_CIE_X, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(ctx->d_cie + YART_N_CIE, YART_CIE_Y, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(ctx->d_cie + 2 * YART_N_CIE, YART_CIE_Z, sizeof(double) * YART_N_CIE, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(ctx->d_smits, YART_SMITS_BASIS, sizeof(double) * 7 * YART_N_BINS, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    set_global_error(std::string("context setup (spectral tables): ") + cudaGetErrorString(e));
+    yart_ctx_destroy(ctx);
+    return YART_ERR_CUDA;
+  }
   *out = ctx;
   return YART_OK;
 }
@@ -513,7 +579,7 @@ void yart_ctx_destroy(yart_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   ctx->free_scene();
-  DevBuf* bufs[] = {&ctx->rays, &ctx->hits_export, &ctx->time, &ctx->wavelength, &ctx->throughput, &ctx->hits, &ctx->contrib,
+  DevBuf* bufs[] = {&ctx->rays, &ctx->hits_export, &ctx->time, &ctx->wavelength, &ctx->throughput, &ctx->hits,
                     &ctx->queue_a, &ctx->queue_b, &ctx->counts, &ctx->work, &ctx->counters, &ctx->film, &ctx->rgba};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -529,6 +595,8 @@ const char* yart_last_error(const yart_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int yart_ctx_set_stream(yart_ctx* ctx, void* cuda_stream) {
   if (!ctx) return YART_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->stream || !ctx->own_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // work queued on the old stream
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   ctx->own_stream = false;
@@ -545,8 +613,16 @@ int yart_ctx_set_builder(yart_ctx* ctx, uint32_t builder) {
   return YART_OK;
 }
 
+static int qbvh_build_device_impl(yart_ctx* ctx, const yart_trimesh* mesh, yart_qbvh** out);
+
 int yart_qbvh_build_device(yart_ctx* ctx, const yart_trimesh* mesh, yart_qbvh** out) {
   if (!ctx) return YART_ERR_INVALID;
+  YART_ABI_GUARD_BEGIN
+  return qbvh_build_device_impl(ctx, mesh, out);
+  YART_ABI_GUARD_END(ctx, "yart_qbvh_build_device")
+}
+
+static int qbvh_build_device_impl(yart_ctx* ctx, const yart_trimesh* mesh, yart_qbvh** out) {
   if (!mesh || !out) {
     ctx->err = "yart_qbvh_build_device: null argument";
     return YART_ERR_INVALID;
@@ -590,18 +666,24 @@ int yart_ctx_synchronize(yart_ctx* ctx) {
   return YART_OK;
 }
 
-int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
-  if (!ctx || !d) return YART_ERR_INVALID;
+static int set_scene_impl(yart_ctx* ctx, const yart_scene_desc* d) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->free_scene();
-  // ---- validation (the reference would panic on these) ----
+  // ---- validation (the reference would panic on these; here a bad descriptor must never become a wild load) ----
   ctx->has_media = false;
+  if ((d->n_objects && !d->objects) || (d->n_lights && !d->lights) || (d->n_meshes && !d->meshes) ||
+      (d->n_groups && !d->groups) || (d->n_materials && !d->materials) || (d->n_textures && !d->textures) ||
+      (d->n_perlins && !d->perlins) || (d->n_images && !d->images)) {
+    ctx->err = "yart_ctx_set_scene: a table pointer is null although its count is not 0";
+    return YART_ERR_INVALID;
+  }
   auto check_obj = [&](const yart_object& o, bool member) -> const char* {
     if (o.kind > YART_OBJ_GROUP) return "unknown object kind";
     if (member && (o.wrap != 0 || (o.kind != YART_OBJ_SPHERE && o.kind != YART_OBJ_BOX)))
       return "group members must be plain spheres or boxes";
-    if (!member && o.material >= d->n_materials) return "object refers to a missing material";
+    // (a GROUP object carries no material of its own: every hit is shaded with its member's)
+    if (o.kind != YART_OBJ_GROUP && o.material >= d->n_materials) return "object refers to a missing material";
     if (o.kind == YART_OBJ_MESH && o.index >= d->n_meshes) return "object refers to a missing mesh";
     if (o.kind == YART_OBJ_GROUP && o.index >= d->n_groups) return "object refers to a missing group";
     if ((o.wrap & YART_WRAP_MEDIUM) && (o.kind == YART_OBJ_MESH || o.kind == YART_OBJ_GROUP))
@@ -626,12 +708,29 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
   }
   for (uint32_t i = 0; i < d->n_textures; ++i) {
     const yart_texture& t = d->textures[i];
-    if (t.kind > YART_TEX_IMAGE || (t.kind == YART_TEX_NOISE && t.perlin >= d->n_perlins) ||
+    if (t.kind > YART_TEX_IMAGE || (t.kind == YART_TEX_NOISE && (t.perlin >= d->n_perlins || t.noise_type > YART_NOISE_NET)) ||
         (t.kind == YART_TEX_IMAGE && t.image >= d->n_images)) {
       ctx->err = "yart_ctx_set_scene: bad texture " + std::to_string(i);
       return YART_ERR_INVALID;
     }
+    if (t.kind == YART_TEX_IMAGE) { // ImageTexture::value indexes width-1 / height-1 (texture.rs:313-345)
+      const yart_image& im = d->images[t.image];
+      if (!im.rgb8 || im.width == 0 || im.height == 0) {
+        ctx->err = "yart_ctx_set_scene: texture " + std::to_string(i) + " refers to an empty image";
+        return YART_ERR_INVALID;
+      }
+    }
   }
+  for (uint32_t i = 0; i < d->n_lights; ++i)
+    if (d->lights[i].kind > YART_OBJ_GROUP) {
+      ctx->err = "yart_ctx_set_scene: light " + std::to_string(i) + ": unknown object kind";
+      return YART_ERR_INVALID;
+    }
+  for (uint32_t i = 0; i < d->n_meshes; ++i)
+    if (d->meshes[i].n_tris && (!d->meshes[i].positions || !d->meshes[i].normals || !d->meshes[i].uvs)) {
+      ctx->err = "yart_ctx_set_scene: mesh " + std::to_string(i) + " has null attribute arrays";
+      return YART_ERR_INVALID;
+    }
   // ---- meshes: QBVH build on the host, flat upload ----
   std::vector<DevMesh> meshes(d->n_meshes);
   std::vector<yart_object> solo(d->n_meshes);
@@ -704,6 +803,10 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
   std::vector<DevGroup> groups(d->n_groups);
   for (uint32_t i = 0; i < d->n_groups; ++i) {
     const yart_group& g = d->groups[i];
+    if (g.n_members && !g.members) {
+      ctx->err = "yart_ctx_set_scene: group " + std::to_string(i) + " has a null member array";
+      return YART_ERR_INVALID;
+    }
     for (uint32_t k = 0; k < g.n_members; ++k)
       if (const char* m = check_obj(g.members[k], true)) {
         ctx->err = std::string("yart_ctx_set_scene: group member: ") + m;
@@ -756,7 +859,8 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
   std::vector<DevImage> images(d->n_images);
   for (uint32_t i = 0; i < d->n_images; ++i) {
     uint8_t* dp;
-    int rc = upload(ctx, d->images[i].rgb8, (size_t)d->images[i].width * d->images[i].height * 3, &dp);
+    const size_t img_bytes = d->images[i].rgb8 ? (size_t)d->images[i].width * d->images[i].height * 3 : 0;
+    int rc = upload(ctx, d->images[i].rgb8, img_bytes, &dp);
     if (rc) {
       ctx->free_scene();
       return rc;
@@ -805,38 +909,60 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
   return YART_OK;
 }
 
-int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint64_t n, double t_min, double t_max,
-                     uint32_t order, uint32_t flags, yart_hit* hits, yart_stats* stats) {
+int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* d) {
   if (!ctx) return YART_ERR_INVALID;
+  if (!d) {
+    ctx->err = "yart_ctx_set_scene: null scene";
+    return YART_ERR_INVALID;
+  }
+  struct Cleanup { // every failing path, exceptions included: nothing half-built stays behind
+    yart_ctx* c;
+    bool armed;
+    ~Cleanup() {
+      if (armed) c->free_scene();
+    }
+  } cleanup{ctx, true};
+  YART_ABI_GUARD_BEGIN
+  const int rc = set_scene_impl(ctx, d);
+  cleanup.armed = rc != YART_OK;
+  return rc;
+  YART_ABI_GUARD_END(ctx, "yart_ctx_set_scene")
+}
+
+static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bool f32, uint64_t n, double t_min, double t_max,
+                            uint32_t order, uint32_t flags, void* hits, yart_stats* stats) {
+  const char* fn = f32 ? "yart_closest_hit_f32" : "yart_closest_hit";
   if (!ctx->have_scene) {
-    ctx->err = "yart_closest_hit: no scene (call yart_ctx_set_scene first)";
+    ctx->err = std::string(fn) + ": no scene (call yart_ctx_set_scene first)";
     return YART_ERR_INVALID;
   }
   if ((n && (!rays || !hits)) || n > 0xFFFFFFF0ull || order > YART_ORDER_NEAR) {
-    ctx->err = "yart_closest_hit: bad argument";
+    ctx->err = std::string(fn) + ": bad argument";
     return YART_ERR_INVALID;
   }
-  if ((flags & YART_FLAG_DEVICE_PTRS) && ((reinterpret_cast<uintptr_t>(rays) & 15u) || (reinterpret_cast<uintptr_t>(hits) & 7u))) {
-    ctx->err = "yart_closest_hit: device ray arrays must be 16-byte aligned (hits: 8)";
+  const uintptr_t ray_align = f32 ? 7u : 15u, hit_align = f32 ? 3u : 7u;
+  if ((flags & YART_FLAG_DEVICE_PTRS) && ((reinterpret_cast<uintptr_t>(rays) & ray_align) || (reinterpret_cast<uintptr_t>(hits) & hit_align))) {
+    ctx->err = std::string(fn) + (f32 ? ": device ray arrays must be 8-byte aligned (hits: 4)" : ": device ray arrays must be 16-byte aligned (hits: 8)");
     return YART_ERR_INVALID;
   }
   if (target != YART_TARGET_WORLD && target >= ctx->n_meshes) {
-    ctx->err = "yart_closest_hit: target is neither a mesh index nor YART_TARGET_WORLD";
+    ctx->err = std::string(fn) + ": target is neither a mesh index nor YART_TARGET_WORLD";
     return YART_ERR_INVALID;
   }
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n == 0) return YART_OK;
+  const size_t ray_bytes = f32 ? sizeof(yart_ray_f32) : sizeof(yart_ray), hit_bytes = f32 ? sizeof(yart_hit_f32) : sizeof(yart_hit);
   const bool dev = (flags & YART_FLAG_DEVICE_PTRS) != 0;
   const bool count = (flags & YART_FLAG_COUNT_VISITS) != 0;
-  const yart_ray* d_rays = rays;
-  yart_hit* d_hits = hits;
+  const void* d_rays = rays;
+  void* d_hits = hits;
   if (!dev) {
-    CUDA_TRY(ctx, ctx->rays.reserve(n * sizeof(yart_ray)));
-    CUDA_TRY(ctx, ctx->hits_export.reserve(n * sizeof(yart_hit)));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rays.p, rays, n * sizeof(yart_ray), cudaMemcpyHostToDevice, ctx->stream));
-    d_rays = ctx->rays.as<yart_ray>();
-    d_hits = ctx->hits_export.as<yart_hit>();
+    CUDA_TRY(ctx, ctx->rays.reserve(n * ray_bytes));
+    CUDA_TRY(ctx, ctx->hits_export.reserve(n * hit_bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rays.p, rays, n * ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_rays = ctx->rays.p;
+    d_hits = ctx->hits_export.p;
   }
   const uint32_t n_list = (target == YART_TARGET_WORLD) ? ctx->scene.n_objects : 1u;
   const size_t work_bytes = ((size_t)n_list + 2) * sizeof(uint32_t);
@@ -852,7 +978,8 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
   solo.cos_theta = 1.0;
   QueryArgs q;
   memset(&q, 0, sizeof(q));
-  q.c.rays = d_rays;
+  if (f32) q.c.rays32 = reinterpret_cast<const yart_ray_f32*>(d_rays);
+  else q.c.rays = reinterpret_cast<const yart_ray*>(d_rays);
   q.c.n_items = n;
   q.c.n_rays = (uint32_t)n;
   q.c.hits = ctx->hits.as<DevHit>();
@@ -881,11 +1008,16 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   int rc = run_passes(ctx, q, &launches);
   if (rc) return rc;
-  k_export<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, d_rays, ctx->hits.as<DevHit>(), d_hits, n);
+  if (f32)
+    k_export_f32<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, export_scene.objects, ctx->hits.as<DevHit>(),
+                                                             reinterpret_cast<yart_hit_f32*>(d_hits), n);
+  else
+    k_export<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, reinterpret_cast<const yart_ray*>(d_rays), ctx->hits.as<DevHit>(),
+                                                         reinterpret_cast<yart_hit*>(d_hits), n);
   launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(yart_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(hits, d_hits, n * hit_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   unsigned long long c[2] = {0, 0};
   if (count) CUDA_TRY(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -903,6 +1035,22 @@ int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint6
   return YART_OK;
 }
 
+int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint64_t n, double t_min, double t_max,
+                     uint32_t order, uint32_t flags, yart_hit* hits, yart_stats* stats) {
+  if (!ctx) return YART_ERR_INVALID;
+  YART_ABI_GUARD_BEGIN
+  return closest_hit_impl(ctx, target, rays, false, n, t_min, t_max, order, flags, hits, stats);
+  YART_ABI_GUARD_END(ctx, "yart_closest_hit")
+}
+
+int yart_closest_hit_f32(yart_ctx* ctx, uint32_t target, const yart_ray_f32* rays, uint64_t n, float t_min, float t_max,
+                         uint32_t order, uint32_t flags, yart_hit_f32* hits, yart_stats* stats) {
+  if (!ctx) return YART_ERR_INVALID;
+  YART_ABI_GUARD_BEGIN
+  return closest_hit_impl(ctx, target, rays, true, n, (double)t_min, (double)t_max, order, flags, hits, stats);
+  YART_ABI_GUARD_END(ctx, "yart_closest_hit_f32")
+}
+
 static int fill_render_params(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, RenderParams& R) {
   if (o->width < 2 || o->height < 2 || o->sample_end < o->sample_begin || o->max_depth == 0 || o->order > YART_ORDER_NEAR ||
       (uint64_t)o->width * o->height > 0x7FFFFFFFull) {
@@ -916,6 +1064,7 @@ static int fill_render_params(yart_ctx* ctx, const yart_camera* cam, const yart_
   R.height = o->height;
   R.max_depth = o->max_depth;
   R.seed = o->seed;
+  R.flags = o->flags & (YART_FLAG_UNBIASED_LIGHT_PICK | YART_FLAG_RUSSIAN_ROULETTE | YART_FLAG_DEPTH_ZERO_BLACK);
   {
     // A trailing run of plain spheres that directly follows a mesh pass is intersected inside k_shade (which
     // reads the ray and the hit anyway) -- saves one read-modify-write pass over the queue per bounce.
@@ -931,9 +1080,57 @@ static int fill_render_params(yart_ctx* ctx, const yart_camera* cam, const yart_
   return YART_OK;
 }
 
+static int render_impl(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, double* film_xyz, yart_stats* stats,
+                       yart_ray* dump_out, uint64_t dump_cap);
+
 int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, double* film_xyz, yart_stats* stats) {
   if (!ctx) return YART_ERR_INVALID;
-  if (!ctx->have_scene || !cam || !o || !film_xyz) {
+  YART_ABI_GUARD_BEGIN
+  if (!film_xyz) {
+    ctx->err = "yart_render: null film";
+    return YART_ERR_INVALID;
+  }
+  return render_impl(ctx, cam, o, film_xyz, stats, nullptr, 0);
+  YART_ABI_GUARD_END(ctx, "yart_render")
+}
+
+int yart_dump_path_rays(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, yart_ray* rays, uint64_t cap,
+                        uint64_t* n_out) {
+  if (!ctx) return YART_ERR_INVALID;
+  YART_ABI_GUARD_BEGIN
+  if (!o || (cap && !rays) || !n_out) {
+    ctx->err = "yart_dump_path_rays: null argument";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const bool dev = (o->flags & YART_FLAG_DEVICE_PTRS) != 0;
+  if (dev && (reinterpret_cast<uintptr_t>(rays) & 15u)) {
+    ctx->err = "yart_dump_path_rays: device ray arrays must be 16-byte aligned";
+    return YART_ERR_INVALID;
+  }
+  yart_ray* d_out = rays;
+  if (!dev && cap) {
+    CUDA_TRY(ctx, ctx->hits_export.reserve(cap * sizeof(yart_ray))); // (a scratch buffer no render kernel touches)
+    d_out = ctx->hits_export.as<yart_ray>();
+  }
+  yart_stats st;
+  const int rc = render_impl(ctx, cam, o, nullptr, &st, d_out, cap);
+  if (rc) return rc;
+  *n_out = st.rays;
+  const uint64_t n_copy = std::min<uint64_t>(st.rays, cap);
+  if (!dev && n_copy) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(rays, d_out, n_copy * sizeof(yart_ray), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return YART_OK;
+  YART_ABI_GUARD_END(ctx, "yart_dump_path_rays")
+}
+
+// film_xyz == nullptr (yart_dump_path_rays): the samples are traced exactly as for a render, the film is a scratch
+// buffer that is thrown away, and every bounce's rays are copied to dump_out.
+static int render_impl(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o, double* film_xyz, yart_stats* stats,
+                       yart_ray* dump_out, uint64_t dump_cap) {
+  if (!ctx->have_scene || !cam || !o) {
     ctx->err = "yart_render: missing scene or null argument";
     return YART_ERR_INVALID;
   }
@@ -944,25 +1141,47 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
   if (stats) memset(stats, 0, sizeof(*stats));
   const uint32_t n_pixels_total = o->width * o->height;
   const uint32_t n_samples = o->sample_end - o->sample_begin;
-  const bool dev = (o->flags & YART_FLAG_DEVICE_PTRS) != 0;
+  const bool dumping = film_xyz == nullptr;
+  const bool dev = !dumping && (o->flags & YART_FLAG_DEVICE_PTRS) != 0;
   const size_t film_bytes = (size_t)n_pixels_total * 3 * sizeof(double);
   double* d_film = film_xyz;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (!dev) {
     CUDA_TRY(ctx, ctx->film.reserve(film_bytes));
     d_film = ctx->film.as<double>();
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_film, film_xyz, film_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (dumping) CUDA_TRY(ctx, cudaMemsetAsync(d_film, 0, film_bytes, ctx->stream));
+    else CUDA_TRY(ctx, cudaMemcpyAsync(d_film, film_xyz, film_bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   uint64_t total_rays = 0, total_paths = 0, launches = 0, trace_launches = 0;
   double trace_ms = 0.0;
   uint32_t deepest = 0;
   if (n_samples > 0) {
-    // batch shape: whole frame x spp_batch, or pixel chunks when the frame alone is too large
+    // Batch shape: whole frame x spp_batch, or pixel chunks when the frame alone is too large.
     // Big batches: every batch pays ~12 ms of fixed cost (the nearly empty tail bounces run at the latency of
-    // their longest ray), so put up to 256 Mi paths in flight (136 B of state each = 36.5 GB of the 180 GB):
-    // david 1080p at 32 / 64 / 128 spp per batch = 1121 / 1146 / 1158 Mrays/s.
+    // their longest ray), so put up to 256 Mi paths in flight -- 112 B of state each (48 ray + 8 time + 8 wavelength
+    // + 8 throughput + 32 hit + 2 x 4 queue) = 30 GB of the 180 GB: david 1080p at 32 / 64 / 128 spp per batch
+    // = 1121 / 1146 / 1158 Mrays/s.  The cap is also bounded by what is actually FREE on the device right now
+    // (minus a margin), so that a busy GPU gets smaller batches instead of a failed cudaMalloc.
     static const int max_paths_log2 = std::max(10, std::min(30, tune_env("YART_TUNE_MAX_PATHS_LOG2", 28)));
-    const uint64_t kMaxPaths = 1ull << max_paths_log2;
+    uint64_t kMaxPaths = 1ull << max_paths_log2;
+    {
+      const uint64_t kStateBytesPerPath = sizeof(yart_ray) + 3 * sizeof(double) + sizeof(DevHit) + 2 * sizeof(uint32_t);
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+      const DevBuf* held[] = {&ctx->rays, &ctx->time, &ctx->wavelength, &ctx->throughput, &ctx->hits, &ctx->queue_a, &ctx->queue_b};
+      uint64_t avail = free_b; // what the state buffers may grow into: free memory + what they already hold
+      for (const DevBuf* b : held) avail += b->cap;
+      const uint64_t margin = (256ull << 20) + (dev ? 0 : film_bytes);
+      const uint64_t fit = avail > margin ? (avail - margin) / kStateBytesPerPath : 0;
+      kMaxPaths = std::min<uint64_t>(kMaxPaths, fit);
+      static const int mem_cap_mb = tune_env("YART_TUNE_STATE_MB", 0); // testing: pretend only this much is free
+      if (mem_cap_mb > 0) kMaxPaths = std::min<uint64_t>(kMaxPaths, ((uint64_t)mem_cap_mb << 20) / kStateBytesPerPath);
+      if (kMaxPaths < 1024) {
+        ctx->err = "yart_render: not enough free device memory for the path state (" + std::to_string(free_b >> 20) +
+                   " MiB free of " + std::to_string(total_b >> 20) + " MiB; 112 bytes per path in flight)";
+        return YART_ERR_NOMEM;
+      }
+    }
     uint32_t spp_batch = o->batch_spp ? o->batch_spp : (uint32_t)std::max<uint64_t>(1, kMaxPaths / n_pixels_total);
     spp_batch = std::min(spp_batch, n_samples);
     uint32_t pix_chunk = n_pixels_total;
@@ -973,7 +1192,6 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
     CUDA_TRY(ctx, ctx->wavelength.reserve(cap * sizeof(double)));
     CUDA_TRY(ctx, ctx->throughput.reserve(cap * sizeof(double)));
     CUDA_TRY(ctx, ctx->hits.reserve(cap * sizeof(DevHit)));
-    CUDA_TRY(ctx, ctx->contrib.reserve(cap * 3 * sizeof(double)));
     CUDA_TRY(ctx, ctx->queue_a.reserve(cap * sizeof(uint32_t)));
     CUDA_TRY(ctx, ctx->queue_b.reserve(cap * sizeof(uint32_t)));
     const uint32_t D = o->max_depth;
@@ -992,7 +1210,6 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
     R.st.wavelength = ctx->wavelength.as<double>();
     R.st.throughput = ctx->throughput.as<double>();
     R.st.hits = ctx->hits.as<DevHit>();
-    R.st.contrib = ctx->contrib.as<double>();
     uint32_t* counts = ctx->counts.as<uint32_t>();
     uint32_t* work = ctx->work.as<uint32_t>();
     std::vector<uint32_t> h_counts(n_counts);
@@ -1039,6 +1256,10 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
           q.counters = ctx->counters.as<unsigned long long>();
           q.near = near;
           q.count = count;
+          if (dump_out) {
+            k_dump_rays<<<stream_grid, 256, 0, ctx->stream>>>(R.st.rays, qa, counts, b, total_rays, dump_out, dump_cap);
+            launches++;
+          }
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1)], ctx->stream));
           rc = run_passes(ctx, q, &trace_launches);
           if (rc) return rc;
@@ -1077,7 +1298,7 @@ int yart_render(yart_ctx* ctx, const yart_camera* cam, const yart_render_opts* o
       }
     }
   }
-  if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(film_xyz, d_film, film_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!dev && !dumping) CUDA_TRY(ctx, cudaMemcpyAsync(film_xyz, d_film, film_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   unsigned long long visit[2] = {0, 0};
   if ((o->flags & YART_FLAG_COUNT_VISITS) && n_samples > 0)
     CUDA_TRY(ctx, cudaMemcpyAsync(visit, ctx->counters.p, sizeof(visit), cudaMemcpyDeviceToHost, ctx->stream));
