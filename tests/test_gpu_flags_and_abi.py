@@ -299,7 +299,8 @@ def test_dump_path_rays_is_what_the_renderer_traces(yart, orc, ctx):
     assert len(common) >= 0.7 * n
     # capped output: the count is still the total
     few, n2 = ctx.dump_path_rays(cam, w, h, 0, spp, 1000, seed=4)
-    assert n2 == n and len(few) == 1000 and np.array_equal(few, rays[:1000])
+    assert n2 == n and len(few) == 1000
+    assert np.isin(key(few), key(rays[:w * h * spp])).all()  # (queue order within a bounce is not reproducible run to run)
     # batches of one sample: same rays, grouped sample by sample
     by1, n3 = ctx.dump_path_rays(cam, w, h, 0, spp, 1 << 20, seed=4, batch_spp=1)
     assert n3 == n and np.array_equal(key(by1), key(rays))
