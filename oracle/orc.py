@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports this module.
-PARITY UNPINNED (see yart_oracle.h): the Rust reference cannot be built here.
+PARITY: unpinned by the reference at the level of single hits / samples (the Rust reference cannot be built
+here); pinned at image level by digests of the reference's own shipped renders (see yart_oracle.h).
 """
 import ctypes as C
 import importlib

@@ -1,9 +1,11 @@
 // yart_oracle.cpp -- CPU ORACLE: a restatement of the reference's hot path in plain C++ (f64,
 // compiled with -ffp-contract=off so no FMA contraction, like rustc's default).
 //
-// TEST INFRASTRUCTURE ONLY (see yart_oracle.h).  PARITY UNPINNED: the Rust reference cannot
-// be built here and holds no golden vectors for this path; this file is pinned by brute
-// force, by SURVEY.md Appendix D and by the reference's own unit tests restated in tests/.
+// TEST INFRASTRUCTURE ONLY (see yart_oracle.h).  PARITY: the Rust reference cannot be built here and
+// holds no golden vectors for this path, so single hits / samples are UNPINNED by the reference; this
+// file is pinned at image level by digests of the reference's own shipped renders and by its scene
+// constants parsed from its source (tests/test_reference_pins.py, tests/test_presets_golden.py), and
+// below that by brute force, SURVEY.md Appendix D and the reference's unit tests restated in tests/.
 //
 // Every function cites the reference lines it follows (paths relative to the reference's
 // raytracer/src/).  Arithmetic is written in the reference's operation order on purpose.

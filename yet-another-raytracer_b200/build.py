@@ -43,7 +43,7 @@ COMPILE_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
     "-Xptxas", "-v",
 ]
-LINK_FLAGS = ["--shared", "-cudart", "shared", "-ldl"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "shared", "-ldl"]
 # tuning knobs: resident blocks per SM / CTA sizes the kernels are compiled for
 for knob in ("YART_TRAVERSE_MIN_BLOCKS", "YART_SHADE_MIN_BLOCKS", "YART_TRACE_THREADS", "YART_SHADE_THREADS"):
     if os.environ.get(knob):
