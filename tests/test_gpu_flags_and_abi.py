@@ -310,3 +310,68 @@ def test_dump_path_rays_is_what_the_renderer_traces(yart, orc, ctx):
         for f in ("t", "u", "v", "prim_id", "obj_id", "front_face"):
             assert np.array_equal(got[f], want[f]), f
     assert (want["obj_id"] != yart.MISS).mean() > 0.4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the one-process multi-GPU renderer and the CLI additions
+# ---------------------------------------------------------------------------------------------------------
+def test_multi_gpu_renderer_progressive_and_against_single_context(yart, ctx):
+    """sharding.MultiGpuRenderer on every visible GPU (1 on the default box, 2+ under `gpurun --gpus N`): chained
+    sample ranges with a read-out in between give the film of one uninterrupted single-context render."""
+    import importlib
+    sh = importlib.import_module("yet-another-raytracer_b200.sharding")
+    preset = yart.ScenePreset("cornell-box", seed=1)
+    ctx.set_scene(preset)
+    w = h = 72
+    cam = preset.camera(w, h)
+    want, st = ctx.render(cam, w, h, 0, 11, seed=8)
+    n = min(yart.device_count(), 4)
+    mg = sh.MultiGpuRenderer(yart, range(n))
+    try:
+        mg.set_scene(preset)
+        sts = mg.render(cam, w, h, 0, 4, seed=8)
+        part = mg.film()                                  # reduce #1: the root keeps the total, the others restart at 0
+        first, _ = ctx.render(cam, w, h, 0, 4, seed=8)
+        assert np.allclose(part, first, rtol=1e-13, atol=1e-13 * np.abs(first).max())
+        sts += mg.render(cam, w, h, 4, 11, seed=8)
+        got = mg.film()                                   # reduce #2 adds only what came since
+        assert sum(s.paths for s in sts) == st.paths
+        if n == 1:
+            assert np.array_equal(got, want)              # one GPU: the very same additions in the same order
+        assert np.allclose(got, want, rtol=1e-13, atol=1e-13 * np.abs(want).max())
+        rgba = mg.finalize(11)
+        assert (np.abs(rgba.astype(int) - ctx.film_finalize(want, 11).astype(int)) <= 1).all()
+        # resuming from a host film
+        mg.load_film(first)
+        mg.render(cam, w, h, 4, 11, seed=8)
+        assert np.allclose(mg.film(), want, rtol=1e-13, atol=1e-13 * np.abs(want).max())
+    finally:
+        mg.close()
+
+
+def test_cli_sampling_flags_gpus_and_checkpoint_guard(yart, tmp_path):
+    import importlib
+    sys.path.insert(0, str(ROOT))
+    cli = importlib.import_module("yart_cli")
+    from PIL import Image
+    base = ["--scene", "cornell-box", "--width", "64", "--seed", "3", "--samples", "16"]
+    a, b, c, ck = (str(tmp_path / n) for n in ("a.png", "b.png", "c.png", "ck.npz"))
+    assert cli.main(base + ["--output", a, "--checkpoint", ck]) == 0
+    assert cli.main(base + ["--output", b, "--unbiased-light-pick"]) == 0
+    ia, ib = np.asarray(Image.open(a)).astype(float), np.asarray(Image.open(b)).astype(float)
+    assert ib[..., :3].mean() < 0.9 * ia[..., :3].mean()   # the unbiased pick is visibly darker (SURVEY A-2)
+    # --gpus: as many as are visible (1 on the default box) must give the same picture up to the last bit of a sum
+    n = min(yart.device_count(), 2)
+    assert cli.main(base + ["--output", c, "--gpus", str(n)]) == 0
+    ic = np.asarray(Image.open(c)).astype(float)
+    assert np.abs(ic - ia).max() <= 1
+    with pytest.raises(SystemExit):
+        cli.main(base + ["--output", c, "--gpus", "99"])
+    # ADVICE r1: a checkpoint holding MORE samples than asked for must not be divided by the smaller count
+    with pytest.raises(SystemExit) as e:
+        cli.main(["--scene", "cornell-box", "--width", "64", "--seed", "3", "--samples", "8", "--output", c,
+                  "--checkpoint", ck, "--resume"])
+    assert "already holds 16" in str(e.value)
+    # and a checkpoint made with another estimator is refused
+    with pytest.raises(SystemExit):
+        cli.main(base + ["--output", c, "--checkpoint", ck, "--resume", "--russian-roulette"])
