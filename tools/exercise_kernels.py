@@ -30,4 +30,23 @@ weird = y.make_rays([(0, 0, 0), (0, 0, 5), (np.nan, 0, 0), (0, 0, 5)], [(0, 0, 0
 for r in (rays, weird, rays[:1], rays[:33]):
     for order in (0, 1):
         ctx.closest_hit(r, 0, 0.0, float("inf"), order)
+# round-2 entry points: f32 records, sampling flags, path-ray dump, device films + a one-rank communicator
+r32 = np.empty(len(rays), dtype=y.abi.RAY_F32_DTYPE)
+r32["origin"], r32["direction"] = rays["origin"], rays["direction"]
+for order in (0, 1):
+    ctx.closest_hit_f32(r32, 0, 0.0, float("inf"), order)
+    ctx.closest_hit_f32(r32[:33], y.TARGET_WORLD, 0.001, float("inf"), order)
+cam = p.camera(48, 32)
+flags = y.FLAG_UNBIASED_LIGHT_PICK | y.FLAG_RUSSIAN_ROULETTE | y.FLAG_DEPTH_ZERO_BLACK
+ctx.render(cam, 48, 32, 0, 3, 50, 1, flags=flags)
+ctx.render(cam, 48, 32, 0, 3, 5, 1, batch_spp=2)
+dumped, n = ctx.dump_path_rays(cam, 48, 32, 0, 2, 1 << 16)
+assert n == len(dumped) > 48 * 32 * 2
+film = ctx.film_create(48, 32)
+ctx.render_device(cam, 48, 32, 0, 2, film, 50, 1)
+comm = y.Comm.from_id(ctx, y.comm_unique_id(), 0, 1)
+comm.film_reduce(film, 48, 32, 0)
+comm.close()
+assert ctx.film_read(film, 48, 32).sum() > 0
+ctx.film_destroy(film)
 print("exercise done")

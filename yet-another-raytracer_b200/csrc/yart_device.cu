@@ -1264,8 +1264,18 @@ static int render_impl(yart_ctx* ctx, const yart_camera* cam, const yart_render_
           rc = run_passes(ctx, q, &trace_launches);
           if (rc) return rc;
           CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * (b - 1) + 1], ctx->stream));
+          static const int dbg_shade_ev = tune_env("YART_DEBUG_BOUNCES", 0);
+          if (dbg_shade_ev) {
+            while (ctx->ev_pool.size() < 4 * (size_t)D) {
+              cudaEvent_t e;
+              CUDA_TRY(ctx, cudaEventCreate(&e));
+              ctx->ev_pool.push_back(e);
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * D + 2 * (b - 1)], ctx->stream));
+          }
           k_shade<<<std::max(1, stream_grid * 256 / kShadeThreads), kShadeThreads, 0, ctx->stream>>>(R, qa, counts + b, qb, counts + b + 1, b);
           launches += 1;
+          if (dbg_shade_ev) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[2 * D + 2 * (b - 1) + 1], ctx->stream));
           std::swap(qa, qb);
           b_done = b;
           // the tail of the bounce loop is nearly empty: look at the live count now and then
@@ -1292,7 +1302,9 @@ static int render_impl(yart_ctx* ctx, const yart_camera* cam, const yart_render_
           if (debug_bounces) {
             float gap = 0.f; // from the end of this bounce's closest-hit stage to the start of the next one
             if (b < b_done) cudaEventElapsedTime(&gap, ctx->ev_pool[2 * (b - 1) + 1], ctx->ev_pool[2 * b]);
-            fprintf(stderr, "bounce %2u: rays %9u  closest-hit %8.3f ms  shade+gap %8.3f ms\n", b, h_counts[b], ms, gap);
+            float shade = 0.f;
+            cudaEventElapsedTime(&shade, ctx->ev_pool[2 * D + 2 * (b - 1)], ctx->ev_pool[2 * D + 2 * (b - 1) + 1]);
+            fprintf(stderr, "bounce %2u: rays %9u  closest-hit %8.3f ms  shade %8.3f ms  shade+gap %8.3f ms\n", b, h_counts[b], ms, shade, gap);
           }
         }
       }
