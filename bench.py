@@ -15,6 +15,8 @@ fixed) and the f64 XYZ films are combined inside every step by the library's own
 scaling number `time_to_image`: the fixed 1024-spp frame split over the N ranks, reduced and finalised to RGBA8.
 `--total-spp S` makes that fixed job the step itself (scaling "strong").
 
+At N = 1 the line also carries `other_configs`: BASELINE.json's C1 / C2 / C4 / C5 once each (device time).
+
 Workload `sweep` (BASELINE.json configs[4]): 16 Mi incoherent rays against the david / sycee QBVH -- the reference's
 bench ray generators (qbvh.rs:949-986): uniform and axis-aligned sets, plus the renderer's own path rays -- in both
 traversal orders, Mrays/s against the fetch roofline.
@@ -335,6 +337,44 @@ def fetch_peaks(ctx):
     return out
 
 
+def other_configs(rig):
+    """BASELINE.json's other configs once each, so that the driver's own record carries them (N = 1 only; ~5 s):
+    C1 cornell-box 400x400x32, C2 bunny preset 1280x720x256, C4 next-week-final 1920x1080 (16 of its 1024 spp),
+    C5 the 16 Mi-ray david sweep (uniform set, both orders).  Device time of the library's own CUDA events; parity of
+    every one of them with the oracle is what tests/test_gpu_baseline_configs.py asserts."""
+    torch, pkg, ctx = rig.torch, rig.pkg, rig.ctx
+    out = {}
+    for tag, scene, w, h, spp, note in (("C1", "cornell-box", 400, 400, 32, "the whole config"),
+                                        ("C2", "bunny", 1280, 720, 256, "the whole config; sycee.obj stands in for the unshipped bunny.obj"),
+                                        ("C4", "next-week-final", 1920, 1080, 16, "16 of the config's 1024 spp")):
+        p = pkg.ScenePreset(scene, seed=SEED)
+        ctx.set_scene(p)
+        cam = p.camera(w, h)
+        film = ctx.film_create(w, h)
+        ctx.render_device(cam, w, h, 0, min(spp, 4), film, MAX_DEPTH, SEED)  # warm
+        ctx.film_clear(film, w, h)
+        st = ctx.render_device(cam, w, h, 0, spp, film, MAX_DEPTH, SEED)
+        ctx.film_destroy(film)
+        out[tag] = {"scene": scene, "width": w, "height": h, "spp": spp, "mrays_per_s": st.rays / st.gpu_ms / 1e3,
+                    "ms": st.gpu_ms, "rays_per_sample": st.rays / st.paths, "note": note}
+    ms_scene = MeshOnlyScene(pkg, "david")
+    ctx.set_scene(ms_scene.desc)
+    rays = sweep_rays(pkg, "david", "uniform", SWEEP_N)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.empty(SWEEP_N * 40, dtype=torch.uint8, device="cuda")
+    c5 = {"mesh": "david", "rays": "uniform, 16 Mi (qbvh.rs:973-986)"}
+    for order, oname in ((pkg.ORDER_NEAR, "near"), (pkg.ORDER_REFERENCE, "reference")):
+        stc = ctx.closest_hit_device(d_rays.data_ptr(), SWEEP_N, d_hits.data_ptr(), 0, 0.0, float("inf"), order, count_visits=True)
+        best = min(ctx.closest_hit_device(d_rays.data_ptr(), SWEEP_N, d_hits.data_ptr(), 0, 0.0, float("inf"), order).gpu_ms
+                   for _ in range(4))
+        bpr = (NODE_BYTES * stc.node_visits + TRI_BYTES * stc.tri_tests) / SWEEP_N + SWEEP_STREAM_BYTES_PER_RAY
+        c5[oname] = {"mrays_per_s": SWEEP_N / best / 1e3, "ms": best, "nodes_per_ray": stc.node_visits / SWEEP_N,
+                     "tris_per_ray": stc.tri_tests / SWEEP_N, "bytes_per_ray": bpr, "algorithmic_gbs": bpr * SWEEP_N / best / 1e6}
+    out["C5"] = c5
+    del d_rays, d_hits
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm: render
 # ------------------------------------------------------------------------------------------------
@@ -482,6 +522,11 @@ def run_render(args):
                                   "C++ restatement of the reference (g++ -O3 -march=x86-64-v3) on %d threads, reference "
                                   "traversal order" % (n_spp, ost.paths, ost.rays, dt, cores)}
 
+    configs = None
+    if rank == 0 and N == 1 and not strong_only and not args.no_other_configs:
+        configs = other_configs(rig)
+        ctx.set_scene(preset)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         fp = fetch_peaks(ctx)
@@ -539,6 +584,7 @@ def run_render(args):
                 "d2h_bytes_per_step": film_bytes, "steps": K2, "ms_per_step": ms2 / K2,
                 "host_result_luminance_sum": luminance},
             "time_to_image": tti,
+            "other_configs": configs,
             "gpu_launches": int(all_launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -706,6 +752,7 @@ def main():
                     help="render: make the step the FIXED job of this many spp split over the GPUs (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-time-to-image", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = (3 if args.total_spp else TOTAL_SPP // SPP_PER_STEP) if args.workload == "render" else 5

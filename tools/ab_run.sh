@@ -2,7 +2,7 @@
 # A/B runner: tools/ab_run.sh "<label>|<env assignments>" ...   -> one line per config: render Mrays/s, k_traverse share, sweep Mrays/s
 for spec in "$@"; do
   label="${spec%%|*}"; envs="${spec#*|}"
-  out=$(env $envs python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-time-to-image 2>/dev/null | python -c "
+  out=$(env $envs python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-time-to-image --no-other-configs 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.readline())
 print('render %.1f Mrays/s  step %.1f ms  trace share %.3f' % (d['value'], d['ms_per_step'], d['roofline']['trace_share_of_step']))")
