@@ -375,3 +375,41 @@ def test_cli_sampling_flags_gpus_and_checkpoint_guard(yart, tmp_path):
     # and a checkpoint made with another estimator is refused
     with pytest.raises(SystemExit):
         cli.main(base + ["--output", c, "--checkpoint", ck, "--resume", "--russian-roulette"])
+
+
+def test_new_entry_points_edge_cases(yart, orc, ctx, mesh_scene):
+    """Degenerate inputs through the round-2 entry points: weird f32 rays, zero-capacity dumps, argument errors."""
+    _, ms, s = mesh_scene("cube")
+    ctx.set_scene(ms.desc)
+    weird = np.zeros(6, dtype=yart.abi.RAY_F32_DTYPE)
+    weird["origin"] = [(0, 0, 0), (0, 0, 5), (np.nan, 0, 0), (0, 0, 5), (0, 0, 5), (0.25, 0.5, 5)]
+    weird["direction"] = [(0, 0, 0), (0, 0, -np.inf), (0, 0, 1), (0, np.nan, -1), (0, 0, -1e-38), (0, 0, -1)]
+    wide = orc.abi.make_rays(weird["origin"].astype(np.float64), weird["direction"].astype(np.float64))
+    want, _ = s.closest_hit(wide, 0, 0.001, INF, 0)
+    for order in (0, 1):
+        got, _ = ctx.closest_hit_f32(weird, 0, 0.001, INF, order)
+        assert np.array_equal(got["prim_id"], want["prim_id"])
+        hit = want["prim_id"] != yart.MISS
+        assert np.array_equal(got["t"][hit], want["t"][hit].astype(np.float32)) and hit[5]
+    with pytest.raises(yart.YartError) as e:
+        ctx.closest_hit_f32(weird, 9)                      # no such mesh
+    assert e.value.code == -1
+    preset = yart.ScenePreset("cornell-box", seed=1)
+    ctx.set_scene(preset)
+    cam = preset.camera(32, 32)
+    none, n = ctx.dump_path_rays(cam, 32, 32, 0, 2, 0)   # capacity 0: only the count comes back
+    _, st = ctx.render(cam, 32, 32, 0, 2)
+    assert len(none) == 0 and n == st.rays
+    same, _ = ctx.render(cam, 32, 32, 0, 2, flags=1 << 20)  # unknown flag bits are ignored, not misread
+    base, _ = ctx.render(cam, 32, 32, 0, 2)
+    assert np.array_equal(same, base)
+    film = ctx.film_create(32, 32)
+    comm = yart.Comm.from_id(ctx, yart.comm_unique_id(), 0, 1)
+    with pytest.raises(yart.YartError):
+        comm.film_reduce([0], 32, 32, 0)                    # null film
+    with pytest.raises(yart.YartError):
+        comm.film_reduce(film, 0, 32, 0)                    # empty frame
+    comm.close()
+    ctx.film_destroy(film)
+    with pytest.raises(yart.YartError):
+        yart.Comm.from_id(ctx, yart.comm_unique_id(), 2, 2)  # rank out of range

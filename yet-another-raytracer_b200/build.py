@@ -30,6 +30,7 @@ CSRC = PKG / "csrc"
 ROOT = PKG.parent
 LIB = PKG / "libyart_b200.so"
 LIB_CHECKED = PKG / "libyart_b200_checked.so"
+HOST_EXE = PKG / "yart"  # the native command-line host (host/yart_main.cpp): the reference's flags on the C ABI
 OBJ_DIR = PKG / "build"
 
 SOURCES = ["host_obj.cpp", "host_qbvh.cpp", "host_presets.cpp", "host_api.cpp", "yart_device.cu",
@@ -91,6 +92,8 @@ def build(force=False, verbose=False, bounds_check=False):
     lib_stamp = PKG / (".build_stamp_checked" if bounds_check else ".build_stamp")
     total = hashlib.sha256("".join(_digest(s, extra) for s in SOURCES).encode()).hexdigest()
     if not force and lib.exists() and lib_stamp.exists() and lib_stamp.read_text().strip() == total:
+        if not bounds_check:
+            build_host()
         return str(lib)
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         results = list(ex.map(lambda s: _compile(s, extra, tag, force), SOURCES))
@@ -110,7 +113,26 @@ def build(force=False, verbose=False, bounds_check=False):
     if verbose:
         print(logs)
     lib_stamp.write_text(total)
+    if not bounds_check:
+        build_host(force=True)
     return str(lib)
+
+
+def build_host(force=False):
+    """g++ (no nvcc, no CUDA headers): host/yart_main.cpp needs nothing but include/yart.h and the shared library."""
+    src = PKG / "host" / "yart_main.cpp"
+    stamp = PKG / ".build_stamp_host"
+    digest = hashlib.sha256(src.read_bytes() + (ROOT / "include" / "yart.h").read_bytes()).hexdigest()
+    if not force and HOST_EXE.exists() and stamp.exists() and stamp.read_text().strip() == digest:
+        return str(HOST_EXE)
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", str(ROOT / "include"), str(src), "-o", str(HOST_EXE),
+           "-L", str(PKG), "-lyart_b200", "-Wl,-rpath,$ORIGIN", "-pthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("host program build failed")
+    stamp.write_text(digest)
+    return str(HOST_EXE)
 
 
 if __name__ == "__main__":
