@@ -413,3 +413,59 @@ def test_new_entry_points_edge_cases(yart, orc, ctx, mesh_scene):
     ctx.film_destroy(film)
     with pytest.raises(yart.YartError):
         yart.Comm.from_id(ctx, yart.comm_unique_id(), 2, 2)  # rank out of range
+
+
+def _rank_process(rank, world, id_path, out_path):
+    """One process per GPU, no torch.distributed: the 128-byte NCCL id travels through a file."""
+    import importlib
+    import time
+    sys.path.insert(0, str(ROOT))
+    y = importlib.import_module("yet-another-raytracer_b200")
+    sh = importlib.import_module("yet-another-raytracer_b200.sharding")
+    ctx = y.Context(rank)
+    if rank == 0:
+        tmp = id_path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(y.comm_unique_id())
+        os.replace(tmp, id_path)
+    else:
+        for _ in range(600):
+            if os.path.exists(id_path):
+                break
+            time.sleep(0.05)
+    uid = open(id_path, "rb").read()
+    comm = y.Comm.from_id(ctx, uid, rank, world)
+    preset = y.ScenePreset("cornell-box", seed=1)
+    ctx.set_scene(preset)
+    w = h = 96
+    cam = preset.camera(w, h)
+    film = ctx.film_create(w, h)
+    lo, hi = sh.shard_range(0, 9, rank, world)
+    ctx.render_device(cam, w, h, lo, hi, film, seed=12)
+    comm.film_reduce(film, w, h, root=0)
+    if rank == 0:
+        np.save(out_path, ctx.film_read(film, w, h))
+    else:
+        ctx.synchronize()
+    comm.close()
+    ctx.film_destroy(film)
+    ctx.close()
+
+
+def test_one_process_per_gpu_comm_from_id(yart, ctx, tmp_path):
+    """The torchrun shape without torch: N processes, one GPU each, yart_comm_unique_id -> a file -> yart_comm_init_rank,
+    sample-range shards, yart_film_reduce; rank 0's film equals the single-GPU film."""
+    if yart.device_count() < 2:
+        pytest.skip("one GPU visible: needs `gpurun --gpus 2` (the single-rank form of from_id is tested above)")
+    import multiprocessing as mp
+    world = 2
+    id_path, out_path = str(tmp_path / "nccl_id.bin"), str(tmp_path / "film.npy")
+    procs = [mp.get_context("spawn").Process(target=_rank_process, args=(r, world, id_path, out_path)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    preset = yart.ScenePreset("cornell-box", seed=1)
+    ctx.set_scene(preset)
+    want, _ = ctx.render(preset.camera(96, 96), 96, 96, 0, 9, seed=12)
+    got = np.load(out_path)
+    assert np.allclose(got, want, rtol=1e-13, atol=1e-13 * np.abs(want).max()) and got.sum() > 0
