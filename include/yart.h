@@ -446,8 +446,8 @@ int yart_dump_path_rays(yart_ctx* ctx, const yart_camera* camera, const yart_ren
 
 /* Roofline denominator for the closest-hit stage ("a measured L2 fetch peak"): every thread
  * fetches `fetches_per_thread` whole 128-byte lines (four 256-bit loads, like one QBVH node visit) at
- * independent random positions of a `table_bytes` table, with the occupancy and cache carveout k_traverse runs
- * at (mode 0) or at full occupancy (mode 1).  Returns the sustained rate in GB/s.  A 7 MB table is the david
+ * independent random positions of a `table_bytes` table, with the occupancy (20 warps per SM) and cache carveout the
+ * traversal kernel runs at (mode 0) or at full occupancy (mode 1).  Returns the sustained rate in GB/s.  A 7 MB table is the david
  * tree: L2-resident, partly L1-resident. */
 int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetches_per_thread, uint32_t mode,
                             double* gbytes_per_s);

@@ -5,6 +5,7 @@
 // contraction, and bit-exact closest-hit parity depends on evaluating (a*b + c*d) the same way.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 #include "../../include/yart.h"

@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
 // ---------------------------------------------------------------------------------------------
 // k_analytic: a run of consecutive non-mesh objects of the list, one thread per queued ray
 // ---------------------------------------------------------------------------------------------
+#ifndef YART_TRACE_NO_ANALYTIC_KERNEL // (the other translation unit that includes this header defines it)
 __global__ void __launch_bounds__(256) k_analytic(const AnalyticParams P) {
   const uint64_t n = P.c.n_items_dev ? (uint64_t)*P.c.n_items_dev : P.c.n_items;
   for (uint64_t item = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; item < n; item += (uint64_t)gridDim.x * blockDim.x) {
@@ -778,5 +779,6 @@ __global__ void __launch_bounds__(256) k_analytic(const AnalyticParams P) {
     if (changed) P.c.hits[ray_id] = h;
   }
 }
+#endif
 
 } // namespace yart

@@ -399,6 +399,11 @@ DevCamera make_camera(const yart_camera& c) { // Camera::new (camera.rs:41-80), 
 }
 
 typedef void (*TraverseKernel)(const TraverseParams);
+} // namespace
+namespace yart {
+TraverseKernel lean_traverse_kernel(bool near, uint32_t max_stack, int ctas_per_sm); // device_trace_lean.cu
+}
+namespace {
 template <bool MIXED>
 TraverseKernel pick_traverse_kernel_m(bool near, bool count, uint32_t max_stack) {
   if (max_stack <= 32) {
@@ -431,6 +436,7 @@ struct QueryArgs {
 int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
   static const int rt = tune_env("YART_TUNE_RT", 8), nt = tune_env("YART_TUNE_NT", 12);
   static const int carve = tune_env("YART_TUNE_CARVEOUT", 35);
+  static const int carve_lean = tune_env("YART_TUNE_CARVEOUT_LEAN", 50);
   static const int mixed = tune_env("YART_TUNE_MIXED", 1); // 0: all-f64 slab tests (same results, slower)
   bool first = true;
   uint32_t i = 0, n_trav = 0;
@@ -475,13 +481,25 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       T.work_counter = q.work_counters + n_trav++;
       T.counters = q.counters;
       for (int k = 0; k < 3; ++k) T.bound[k] = m.bound[k];
-      TraverseKernel k = pick_traverse_kernel(q.near, q.count, ctx->max_stack, mixed != 0);
+      // k_traverse_lean (device_trace_lean.cu): the same traversal with the f64-only state in shared memory -- 96
+      // registers, FIVE 128-thread CTAs per SM (20 warps) instead of four: +7 % on the david render, +6 % on the sweep.
+      // YART_TUNE_LEAN=0 selects k_traverse (which also serves visit counting and the all-f64 slab variant).
+      static const int lean = tune_env("YART_TUNE_LEAN", 5);
+      static const int lean_stack24 = tune_env("YART_TUNE_LEAN_STACK24", 1);
+      // (the reference-order instantiation of the lean kernel spills 150 B at 96 registers and is 5 % SLOWER than
+      // k_traverse on the sweep -- 2,074 vs 2,188 Mrays/s -- so only the near-first order, the default everywhere, uses it;
+      // YART_TUNE_LEAN_REF=1 forces it for both)
+      static const int lean_ref = tune_env("YART_TUNE_LEAN_REF", 0);
+      const bool use_lean = lean && mixed && !q.count && (q.near || lean_ref);
+      TraverseKernel k = use_lean ? yart::lean_traverse_kernel(q.near, (lean_stack24 || ctx->max_stack > 24) ? ctx->max_stack : 25u, lean)
+                                  : pick_traverse_kernel(q.near, q.count, ctx->max_stack, mixed != 0);
       // occupancy query + carveout once per kernel variant (they cost tens of microseconds of host time,
       // which is the whole budget of a deep bounce)
       int& per_sm = ctx->traverse_blocks[(const void*)k];
       if (per_sm == 0) {
         // leave everything the stacks do not need to L1: the tree's upper levels live there
-        cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        // (the lean kernel keeps 22-42 KB of shared memory per CTA: five CTAs need the 132 KB configuration)
+        cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributePreferredSharedMemoryCarveout, use_lean ? carve_lean : carve);
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(k), kTraceThreads, 0));
         per_sm = std::max(per_sm, 1);
       }
@@ -1406,7 +1424,7 @@ int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetche
   float ms = 0.f;
   size_t threads = 0;
   if (e == cudaSuccess) {
-    static const int carve = tune_env("YART_TUNE_CARVEOUT", 35);
+    static const int carve = tune_env("YART_TUNE_CARVEOUT_LEAN", 50);
     auto run = [&](auto kernel, int block, bool set_carve) {
       if (set_carve) cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout, carve);
       int per_sm = 1;
@@ -1418,9 +1436,9 @@ int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetche
       kernel<<<grid, block, 0, ctx->stream>>>(table.as<float4>(), n_lines, fetches_per_thread, sink.as<float>());
       cudaEventRecord(ctx->ev1, ctx->stream);
     };
-    // mode 0: 128-thread CTAs, 4 per SM -- 16 warps per SM like k_traverse (its register budget, not this
+    // mode 0: 128-thread CTAs, 5 per SM -- 20 warps per SM like k_traverse_lean (its register budget, not this
     // kernel's, is what limits it), same carveout; mode 1: whatever fits
-    if (mode == 0) run(k_fetch_peak<128, 4>, 128, true);
+    if (mode == 0) run(k_fetch_peak<128, 5>, 128, true);
     else run(k_fetch_peak<256, 8>, 256, false);
     e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
