@@ -549,7 +549,7 @@ def run_render(args):
                 "fetch_peaks": dict(fp, **{
                     "frac_of_l2_resident_fetch_peak": (achieved / fp["scene_sized_l2_resident_gbs"]) if achieved else None,
                     "frac_of_l1_resident_fetch_peak": (achieved / fp["l1_resident_gbs"]) if achieved else None,
-                    "note": "yart_measure_fetch_peak mode 1 (full occupancy; the roof) and mode 0 (k_traverse's 16 warps/SM): every "
+                    "note": "yart_measure_fetch_peak mode 1 (full occupancy; the roof) and mode 0 (k_traverse_lean's 20 warps/SM): every "
                             "lane fetches whole 128-B lines (four LDG.E.256) at independent random positions of an L1-sized / "
                             "scene-sized table"}),
                 "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,

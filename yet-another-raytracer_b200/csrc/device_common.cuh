@@ -138,6 +138,13 @@ struct DevMesh {
   uint32_t max_stack;
   uint32_t n_nodes, n_tris;
   double bound[3];      // max |coordinate| per axis
+  // Compact nodes (k_pack_nodes): the same tree, node for node, as 64-byte records -- the 24 box planes as 16-bit
+  // offsets from the mesh's bounding-box corner in units of cscale (lower planes rounded down, upper planes up: the
+  // quantised box CONTAINS the exact one and is at most one unit larger on each side) + the four child words.
+  // Null when the mesh is not eligible (see set_scene).
+  const uint4* cnodes;
+  float corigin[3];     // the corner (an exact f32)
+  float cscale;         // 2^e
 };
 
 // A flat 4-wide tree over the members of a BVHNode group (spheres / boxes).  Same 128-byte node

@@ -282,6 +282,8 @@ struct TraverseParams {
   const float4* nodes;
   const float4* tris;
   const float4* leafgeo;      // packed per-leaf vertex blocks (DevMesh::leafgeo)
+  const uint4* cnodes;        // compact 64-byte nodes (DevMesh::cnodes), null = not available
+  float corigin[3], cscale;
   uint32_t root;
   uint32_t obj_index;         // world object index recorded with a hit
   uint32_t wrap;              // YART_WRAP_ROTATE_Y / TRANSLATE of this instance

@@ -11,7 +11,26 @@
 
 namespace yart {
 
-template <bool NEAR, int STACK, int MIN_BLOCKS>
+// COMPACT: inner nodes are read from DevMesh::cnodes (64 bytes = TWO sectors per visit instead of four; the kernel is
+// bound by L1 data-pipe wavefronts once 20 warps are resident).  The 24 planes of a node are 16-bit offsets q from the
+// mesh's bounding-box corner G in units of s = 2^e: plane = G + q s.  Per ray and axis the slab value is one FMA,
+//     t = fma(m, A, B),   m = float(2^23 + q) (one PRMT builds it from the 16-bit field),  A = s inv32,
+//     B = fma(-2^23, A, fma(G, inv32, c32)),
+// and it differs from the exact-real slab value of that quantised plane by at most
+//     2^-24 |t| + 2^-21 (Bmax + |o|) |inv| + |A| / 2
+// (inv32, c32 carry 2^-24 relative each; the fma that forms B rounds a number of size 2^23 |A|, i.e. by up to |A| / 2; the
+// 2^23 A in m A cancels against it exactly).  The quantised box CONTAINS the exact f32 box, and the same box shrunk by
+// one grid step (|A| in t) on every side is CONTAINED in it (k_pack_nodes).  Per node and axis four shifted constants
+//     B - |A| (entry, outer)   B + 3|A| (entry, inner)   B + |A| (exit, outer)   B - 3|A| (exit, inner)
+// (each rounds by another |A| / 2 at most) give slab values that bracket the exact box's PER AXIS -- the grid step in t
+// is s / |d_a|, huge on an axis the ray is nearly parallel to, so one common margin would be useless:
+//     outer entry <= exact entry <= inner entry,   inner exit <= exact exit <= outer exit   (up to the first two terms),
+// and with E = R (|far| + |near|) + 2^-20 max (Bmax + |o|) |inv|  (R = 2^-22; margins doubled like in k_traverse):
+//     far_outer - near_outer < -E   =>  even the containing box is missed  =>  the reference's far > near fails;
+//     far_inner - near_inner >  E   =>  even the contained box is hit      =>  the reference's test passes;
+// only what lies in between -- the ray passes within ~4 grid steps of deciding otherwise -- is settled by the exact f64
+// test on the exact 128-byte node.  Results are bit-identical to the reference either way.
+template <bool NEAR, int STACK, int MIN_BLOCKS, bool COMPACT>
 __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(const TraverseParams P) {
   constexpr bool MIXED = true;
   __shared__ uint32_t s_stack[STACK + 1][kTraceThreads];
@@ -69,6 +88,8 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
   uint32_t best_prim = YART_MISS; // YART_MISS = this mesh has not produced a hit
   bool exhausted = false;         // the global queue is empty
   // MIXED: the ray as f32 slab coefficients t = b*inv + c, and the absolute part of the error bound
+  // !COMPACT: t = fma(b, ixf, cxf) per slab, amax2 = the absolute error term.  COMPACT: ixf.. hold A, cxf.. hold B,
+  // amax2 the constant part of E.
   float ixf = 0, iyf = 0, izf = 0, cxf = 0, cyf = 0, czf = 0, amax2 = 0, t_best_f = 0;
   const float t_min_f = (float)t_min;
 
@@ -198,6 +219,19 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
             const bool ok = fabsf(ixf) > lo && fabsf(ixf) < hi && fabsf(iyf) > lo && fabsf(iyf) < hi && fabsf(izf) > lo &&
                             fabsf(izf) < hi && fabsf(cxf) < hi && fabsf(cyf) < hi && fabsf(czf) < hi && amax2 < hi;
             if (!ok) pos |= 8u;
+            if (COMPACT) {
+              const float ax = P.cscale * ixf, ay = P.cscale * iyf, az = P.cscale * izf; // (exact: a power of two)
+              const float bx = fmaf(-8388608.f, ax, fmaf(P.corigin[0], ixf, cxf));
+              const float by = fmaf(-8388608.f, ay, fmaf(P.corigin[1], iyf, cyf));
+              const float bz = fmaf(-8388608.f, az, fmaf(P.corigin[2], izf, czf));
+              const float q = fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az)));
+              const float aterm = __double2float_ru(a * (1.0 / 1048576.0)); // 2^-20 * a
+              const bool okc = fabsf(bx) < hi && fabsf(by) < hi && fabsf(bz) < hi && q < hi && q > 0.f && aterm < hi;
+              if (!okc) pos |= 8u;
+              ixf = ax; iyf = ay; izf = az;
+              cxf = bx; cyf = by; czf = bz;
+              amax2 = aterm;
+            }
             t_best_f = (float)t_best;
           }
           cur = P.root;
@@ -224,49 +258,109 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
       }
       if (has_node) {
         YART_CHECK(cur < P.n_nodes);
-        const float4* nd = nodes + (size_t)cur * 8;
-        // the whole 128-byte node in four 256-bit loads, all in flight together
-        const F8 sx8 = ldg256(nd + 0), sy8 = ldg256(nd + 2), sz8 = ldg256(nd + 4), cm8 = ldg256(nd + 6);
-        const uint4 ch = make_uint4(__float_as_uint(cm8.lo.x), __float_as_uint(cm8.lo.y), __float_as_uint(cm8.lo.z),
-                                    __float_as_uint(cm8.lo.w));
-        const uint32_t axes = __float_as_uint(cm8.hi.x);
-        uint32_t hitmask = 0;
-        if (MIXED && !(pos & 8u)) {
-          // Conservative f32 test.  Per slab t32 = fma(b, inv32, c32); near32 / far32 are the max / min over
-          // the entry / exit planes with t_min / t_best folded in.  With R = 2^-22 and A as above,
-          // |near32 - near64| <= R|near32| + A and the same for far, so
-          //   far32 - near32 >  R(|far32| + |near32|) + 2A  =>  far64 > near64   (the reference pushes)
-          //   far32 - near32 < -R(|far32| + |near32|) - 2A  =>  far64 < near64   (the reference does not)
-          // and everything in between (also any inf / NaN) is settled by the exact f64 test.
-          const bool px = (pos & 1u) != 0, py = (pos & 2u) != 0, pz = (pos & 4u) != 0;
-#define YART_SEL4(P_, A, B) make_float4((P_) ? A.x : B.x, (P_) ? A.y : B.y, (P_) ? A.z : B.z, (P_) ? A.w : B.w)
-          const float4 nx = YART_SEL4(px, sx8.lo, sx8.hi), fx = YART_SEL4(px, sx8.hi, sx8.lo);
-          const float4 ny = YART_SEL4(py, sy8.lo, sy8.hi), fy = YART_SEL4(py, sy8.hi, sy8.lo);
-          const float4 nz = YART_SEL4(pz, sz8.lo, sz8.hi), fz = YART_SEL4(pz, sz8.hi, sz8.lo);
-#undef YART_SEL4
-          uint32_t amb = 0;
-#define YART_BOX_F32(K, C)                                                                                  \
-  {                                                                                                         \
-    const float tn = fmaxf(fmaxf(t_min_f, fmaf(nx.C, ixf, cxf)), fmaxf(fmaf(ny.C, iyf, cyf), fmaf(nz.C, izf, czf))); \
-    const float tf = fminf(fminf(t_best_f, fmaf(fx.C, ixf, cxf)), fminf(fmaf(fy.C, iyf, cyf), fmaf(fz.C, izf, czf))); \
-    const float g = tf - tn;                                                                                \
-    const float e = fmaf(fabsf(tf) + fabsf(tn), 2.384185791015625e-7f, amax2);                              \
-    hitmask |= (g > e) ? (1u << (K)) : 0u;                                                                  \
-    amb |= ((g > e) || (g < -e)) ? 0u : (1u << (K));                                                        \
+        uint4 ch;
+        uint32_t axes, hitmask = 0;
+        if (COMPACT) {
+          const float4* cn = reinterpret_cast<const float4*>(P.cnodes) + (size_t)cur * 4;
+          const F8 c0 = ldg256(cn), c1 = ldg256(cn + 2); // the whole 64-byte node: two sectors
+          // child words: ids with the node's axes in bits 29-30 of the first three (k_pack_nodes)
+          const uint32_t w0 = __float_as_uint(c1.hi.x), w1 = __float_as_uint(c1.hi.y), w2 = __float_as_uint(c1.hi.z),
+                         w3 = __float_as_uint(c1.hi.w);
+          ch = make_uint4(w0 & 0x9FFFFFFFu, w1 & 0x9FFFFFFFu, w2 & 0x9FFFFFFFu, w3);
+          axes = ((w0 >> 29) & 3u) | (((w1 >> 29) & 3u) << 2) | (((w2 >> 29) & 3u) << 4);
+          const uint32_t present = ((w0 | 0x60000000u) != 0xFFFFFFFFu ? 1u : 0u) | ((w1 | 0x60000000u) != 0xFFFFFFFFu ? 2u : 0u) |
+                                   ((w2 | 0x60000000u) != 0xFFFFFFFFu ? 4u : 0u) | (w3 != 0xFFFFFFFFu ? 8u : 0u);
+          if (!(pos & 8u)) {
+            const bool px = (pos & 1u) != 0, py = (pos & 2u) != 0, pz = (pos & 4u) != 0;
+            // entry / exit planes: the lower or the upper 16-bit fields, by the sign of the direction (12 selects)
+            const uint32_t xl01 = __float_as_uint(c0.lo.x), xl23 = __float_as_uint(c0.lo.y), xh01 = __float_as_uint(c0.lo.z),
+                           xh23 = __float_as_uint(c0.lo.w), yl01 = __float_as_uint(c0.hi.x), yl23 = __float_as_uint(c0.hi.y),
+                           yh01 = __float_as_uint(c0.hi.z), yh23 = __float_as_uint(c0.hi.w), zl01 = __float_as_uint(c1.lo.x),
+                           zl23 = __float_as_uint(c1.lo.y), zh01 = __float_as_uint(c1.lo.z), zh23 = __float_as_uint(c1.lo.w);
+            const uint32_t nx01 = px ? xl01 : xh01, nx23 = px ? xl23 : xh23, fx01 = px ? xh01 : xl01, fx23 = px ? xh23 : xl23;
+            const uint32_t ny01 = py ? yl01 : yh01, ny23 = py ? yl23 : yh23, fy01 = py ? yh01 : yl01, fy23 = py ? yh23 : yl23;
+            const uint32_t nz01 = pz ? zl01 : zh01, nz23 = pz ? zl23 : zh23, fz01 = pz ? zh01 : zl01, fz23 = pz ? zh23 : zl23;
+            uint32_t amb = 0;
+            // the four shifted constants per axis (see the bound above)
+            const float hx = fabsf(ixf), hy = fabsf(iyf), hz = fabsf(izf);
+            const float bxno = cxf - hx, bxni = fmaf(3.f, hx, cxf), bxfo = cxf + hx, bxfi = fmaf(-3.f, hx, cxf);
+            const float byno = cyf - hy, byni = fmaf(3.f, hy, cyf), byfo = cyf + hy, byfi = fmaf(-3.f, hy, cyf);
+            const float bzno = czf - hz, bzni = fmaf(3.f, hz, czf), bzfo = czf + hz, bzfi = fmaf(-3.f, hz, czf);
+            // float(2^23 + q) from a 16-bit field: bytes {q.lo, q.hi, 0x00, 0x4B}
+#define YART_MAGIC(W, HALF) __uint_as_float(__byte_perm((W), 0x4B000000u, (HALF) ? 0x7432u : 0x7410u))
+#define YART_BOX_Q(K, NXW, NYW, NZW, FXW, FYW, FZW, HALF)                                                              \
+  {                                                                                                                    \
+    const float mnx = YART_MAGIC(NXW, HALF), mny = YART_MAGIC(NYW, HALF), mnz = YART_MAGIC(NZW, HALF);                 \
+    const float mfx = YART_MAGIC(FXW, HALF), mfy = YART_MAGIC(FYW, HALF), mfz = YART_MAGIC(FZW, HALF);                 \
+    const float tno = fmaxf(fmaxf(t_min_f, fmaf(mnx, ixf, bxno)), fmaxf(fmaf(mny, iyf, byno), fmaf(mnz, izf, bzno)));  \
+    const float tfo = fminf(fminf(t_best_f, fmaf(mfx, ixf, bxfo)), fminf(fmaf(mfy, iyf, byfo), fmaf(mfz, izf, bzfo))); \
+    const float tni = fmaxf(fmaxf(t_min_f, fmaf(mnx, ixf, bxni)), fmaxf(fmaf(mny, iyf, byni), fmaf(mnz, izf, bzni)));  \
+    const float tfi = fminf(fminf(t_best_f, fmaf(mfx, ixf, bxfi)), fminf(fmaf(mfy, iyf, byfi), fmaf(mfz, izf, bzfi))); \
+    const float e = fmaf(fabsf(tfo) + fabsf(tno), 2.384185791015625e-7f, amax2);                                       \
+    const bool hit = (tfi - tni) > e, miss = (tfo - tno) < -e;                                                         \
+    hitmask |= hit ? (1u << (K)) : 0u;                                                                                 \
+    amb |= (hit || miss) ? 0u : (1u << (K));                                                                           \
   }
-          YART_BOX_F32(0, x)
-          YART_BOX_F32(1, y)
-          YART_BOX_F32(2, z)
-          YART_BOX_F32(3, w)
-#undef YART_BOX_F32
-          if (amb) {
-            const uint32_t exact = box4_ieee<NEAR>(nd, s_ray[0][tid], s_ray[1][tid], s_ray[2][tid], 1.0 / s_ray[3][tid], 1.0 / s_ray[4][tid],
-                                                   1.0 / s_ray[5][tid], t_min, t_best);
-            hitmask = (hitmask & ~amb) | (exact & amb);
+            YART_BOX_Q(0, nx01, ny01, nz01, fx01, fy01, fz01, 0)
+            YART_BOX_Q(1, nx01, ny01, nz01, fx01, fy01, fz01, 1)
+            YART_BOX_Q(2, nx23, ny23, nz23, fx23, fy23, fz23, 0)
+            YART_BOX_Q(3, nx23, ny23, nz23, fx23, fy23, fz23, 1)
+#undef YART_BOX_Q
+#undef YART_MAGIC
+            hitmask &= present;
+            amb &= present;
+            if (amb) {
+              const uint32_t exact = box4_ieee<NEAR>(nodes + (size_t)cur * 8, s_ray[0][tid], s_ray[1][tid], s_ray[2][tid], 1.0 / s_ray[3][tid],
+                                                     1.0 / s_ray[4][tid], 1.0 / s_ray[5][tid], t_min, t_best);
+              hitmask = (hitmask & ~amb) | (exact & amb);
+            }
+          } else {
+            hitmask = box4_ieee<NEAR>(nodes + (size_t)cur * 8, s_ray[0][tid], s_ray[1][tid], s_ray[2][tid], 1.0 / s_ray[3][tid],
+                                      1.0 / s_ray[4][tid], 1.0 / s_ray[5][tid], t_min, t_best);
           }
         } else {
-          hitmask = box4_ieee<NEAR>(nd, s_ray[0][tid], s_ray[1][tid], s_ray[2][tid], 1.0 / s_ray[3][tid], 1.0 / s_ray[4][tid],
-                                    1.0 / s_ray[5][tid], t_min, t_best);
+          const float4* nd = nodes + (size_t)cur * 8;
+          // the whole 128-byte node in four 256-bit loads, all in flight together
+          const F8 sx8 = ldg256(nd + 0), sy8 = ldg256(nd + 2), sz8 = ldg256(nd + 4), cm8 = ldg256(nd + 6);
+          ch = make_uint4(__float_as_uint(cm8.lo.x), __float_as_uint(cm8.lo.y), __float_as_uint(cm8.lo.z), __float_as_uint(cm8.lo.w));
+          axes = __float_as_uint(cm8.hi.x);
+          if (MIXED && !(pos & 8u)) {
+            // Conservative f32 test.  Per slab t32 = fma(b, inv32, c32); near32 / far32 are the max / min over
+            // the entry / exit planes with t_min / t_best folded in.  With R = 2^-22 and A as above,
+            // |near32 - near64| <= R|near32| + A and the same for far, so
+            //   far32 - near32 >  R(|far32| + |near32|) + 2A  =>  far64 > near64   (the reference pushes)
+            //   far32 - near32 < -R(|far32| + |near32|) - 2A  =>  far64 < near64   (the reference does not)
+            // and everything in between (also any inf / NaN) is settled by the exact f64 test.
+            const bool px = (pos & 1u) != 0, py = (pos & 2u) != 0, pz = (pos & 4u) != 0;
+  #define YART_SEL4(P_, A, B) make_float4((P_) ? A.x : B.x, (P_) ? A.y : B.y, (P_) ? A.z : B.z, (P_) ? A.w : B.w)
+            const float4 nx = YART_SEL4(px, sx8.lo, sx8.hi), fx = YART_SEL4(px, sx8.hi, sx8.lo);
+            const float4 ny = YART_SEL4(py, sy8.lo, sy8.hi), fy = YART_SEL4(py, sy8.hi, sy8.lo);
+            const float4 nz = YART_SEL4(pz, sz8.lo, sz8.hi), fz = YART_SEL4(pz, sz8.hi, sz8.lo);
+  #undef YART_SEL4
+            uint32_t amb = 0;
+  #define YART_BOX_F32(K, C)                                                                                  \
+    {                                                                                                         \
+      const float tn = fmaxf(fmaxf(t_min_f, fmaf(nx.C, ixf, cxf)), fmaxf(fmaf(ny.C, iyf, cyf), fmaf(nz.C, izf, czf))); \
+      const float tf = fminf(fminf(t_best_f, fmaf(fx.C, ixf, cxf)), fminf(fmaf(fy.C, iyf, cyf), fmaf(fz.C, izf, czf))); \
+      const float g = tf - tn;                                                                                \
+      const float e = fmaf(fabsf(tf) + fabsf(tn), 2.384185791015625e-7f, amax2);                              \
+      hitmask |= (g > e) ? (1u << (K)) : 0u;                                                                  \
+      amb |= ((g > e) || (g < -e)) ? 0u : (1u << (K));                                                        \
+    }
+            YART_BOX_F32(0, x)
+            YART_BOX_F32(1, y)
+            YART_BOX_F32(2, z)
+            YART_BOX_F32(3, w)
+  #undef YART_BOX_F32
+            if (amb) {
+              const uint32_t exact = box4_ieee<NEAR>(nd, s_ray[0][tid], s_ray[1][tid], s_ray[2][tid], 1.0 / s_ray[3][tid], 1.0 / s_ray[4][tid],
+                                                     1.0 / s_ray[5][tid], t_min, t_best);
+              hitmask = (hitmask & ~amb) | (exact & amb);
+            }
+          } else {
+            hitmask = box4_ieee<NEAR>(nd, s_ray[0][tid], s_ray[1][tid], s_ray[2][tid], 1.0 / s_ray[3][tid], 1.0 / s_ray[4][tid],
+                                      1.0 / s_ray[5][tid], t_min, t_best);
+          }
         }
         // push_hit_children (qbvh.rs:18-31) in the order ORDER_TABLE[4*pos[top] + 2*pos[left] + pos[right]]
         // (qbvh.rs:14-16, 521-524) gives.  The table has structure: bit `top` says whether the left pair
@@ -297,7 +391,7 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
 
     // =============== phase C: one leaf (qbvh.rs:413-490) ========================================
     if (cur >= 0x80000000u) {
-      const uint32_t count = (cur >> 27) & 0xFu;
+      const uint32_t count = COMPACT ? ((cur >> 27) & 3u) + 1u : (cur >> 27) & 0xFu; // (compact child words keep count - 1)
       const uint32_t first = cur & 0x7FFFFFFu;
       YART_CHECK(count >= 1 && count <= 4 && first + count <= P.n_tris);
       const double ox = s_ray[0][tid], oy = s_ray[1][tid], oz = s_ray[2][tid];
@@ -387,14 +481,15 @@ typedef void (*TraverseKernel)(const TraverseParams);
 // (visit counting and the all-f64 slab variant stay with k_traverse)
 // ctas_per_sm: 5 (96 registers, 20 warps per SM) or 6 (80 registers, 24 warps).  The stack is sized to the tree:
 // 24 entries cover 7 node levels (3 * height + 1 = 22: david, sycee), 32 cover 10, 64 the reference's own limit.
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool COMPACT>
 static TraverseKernel pick_lean(bool near, uint32_t max_stack) {
-  if (max_stack <= 24) return near ? k_traverse_lean<true, 24, MIN_BLOCKS> : k_traverse_lean<false, 24, MIN_BLOCKS>;
-  if (max_stack <= 32) return near ? k_traverse_lean<true, 32, MIN_BLOCKS> : k_traverse_lean<false, 32, MIN_BLOCKS>;
-  return near ? k_traverse_lean<true, 64, MIN_BLOCKS> : k_traverse_lean<false, 64, MIN_BLOCKS>;
+  if (max_stack <= 24) return near ? k_traverse_lean<true, 24, MIN_BLOCKS, COMPACT> : k_traverse_lean<false, 24, MIN_BLOCKS, COMPACT>;
+  if (max_stack <= 32) return near ? k_traverse_lean<true, 32, MIN_BLOCKS, COMPACT> : k_traverse_lean<false, 32, MIN_BLOCKS, COMPACT>;
+  return near ? k_traverse_lean<true, 64, MIN_BLOCKS, COMPACT> : k_traverse_lean<false, 64, MIN_BLOCKS, COMPACT>;
 }
-TraverseKernel lean_traverse_kernel(bool near, uint32_t max_stack, int ctas_per_sm) {
-  return ctas_per_sm >= 6 ? pick_lean<6>(near, max_stack) : pick_lean<5>(near, max_stack);
+TraverseKernel lean_traverse_kernel(bool near, uint32_t max_stack, int ctas_per_sm, bool compact) {
+  if (compact) return pick_lean<5, true>(near, max_stack);
+  return ctas_per_sm >= 6 ? pick_lean<6, false>(near, max_stack) : pick_lean<5, false>(near, max_stack);
 }
 
 } // namespace yart

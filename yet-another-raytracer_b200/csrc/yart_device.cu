@@ -113,6 +113,47 @@ __global__ void __launch_bounds__(256) k_pack_leaves(const FlatNode* __restrict_
   }
 }
 
+// DevMesh::cnodes from the flattened tree, one thread per node.  Word layout of a 64-byte compact node (two 32-byte
+// sectors; every 32-bit word holds the 16-bit values of two children, child 2j in the low half, 2j+1 in the high half):
+//   sector 0: x lower planes (children 01, 23), x upper planes (01, 23), y lower (01, 23), y upper (01, 23)
+//   sector 1: z lower (01, 23), z upper (01, 23), then the four child words exactly as in FlatNode::child, with the node's
+//             three split axes stowed in the otherwise unused bits 29-30 of the first three words (child ids use bits
+//             0-26 + the leaf flag 31 + the leaf count 27-28 as count-1).  0xFFFFFFFF = absent child, as in FlatNode.
+// Quantisation, exact in f64: lower plane -> floor((b - origin) / scale), upper plane -> ceil(...): the quantised box
+// contains the exact box, and shrinking it by one unit on every side gives a box contained in the exact one.
+__global__ void __launch_bounds__(256) k_pack_nodes(const FlatNode* __restrict__ nodes, uint32_t n_nodes, float ox, float oy, float oz,
+                                                     float scale, uint4* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const FlatNode nd = nodes[i];
+  const double o[3] = {(double)ox, (double)oy, (double)oz}, inv = 1.0 / (double)scale; // (scale is a power of two)
+  const float* lo[3] = {nd.min_x, nd.min_y, nd.min_z};
+  const float* hi[3] = {nd.max_x, nd.max_y, nd.max_z};
+  uint32_t w[16];
+  for (int a = 0; a < 3; ++a)
+    for (int pair = 0; pair < 2; ++pair) {
+      uint32_t ql[2], qh[2];
+      for (int h = 0; h < 2; ++h) {
+        const int k = pair * 2 + h;
+        const bool present = nd.child[k] != 0xFFFFFFFFu;
+        const double l = floor(((double)lo[a][k] - o[a]) * inv), u = ceil(((double)hi[a][k] - o[a]) * inv);
+        ql[h] = present ? (uint32_t)fmin(fmax(l, 0.0), 65535.0) : 65535u; // (an absent child: an inverted box)
+        qh[h] = present ? (uint32_t)fmin(fmax(u, 0.0), 65535.0) : 0u;
+      }
+      w[a * 4 + pair] = ql[0] | (ql[1] << 16);
+      w[a * 4 + 2 + pair] = qh[0] | (qh[1] << 16);
+    }
+  for (int k = 0; k < 4; ++k) {
+    uint32_t c = nd.child[k];
+    if (c != 0xFFFFFFFFu) {
+      if (c >> 31) c = 0x80000000u | ((((c >> 27) & 0xFu) - 1u) << 27) | (c & 0x7FFFFFFu); // leaf count 1..4 -> 2 bits
+      if (k < 3) c |= ((nd.axes >> (2 * k)) & 3u) << 29;                                    // top, left, right axis
+    }
+    w[12 + k] = c;
+  }
+  for (int j = 0; j < 4; ++j) out[(size_t)i * 4 + j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+
 // yart_measure_fetch_peak: independent random 128-byte line fetches (one QBVH node visit = four LDG.E.256)
 template <int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_fetch_peak(const float4* __restrict__ table, uint32_t n_lines, uint32_t iters,
@@ -401,7 +442,7 @@ DevCamera make_camera(const yart_camera& c) { // Camera::new (camera.rs:41-80), 
 typedef void (*TraverseKernel)(const TraverseParams);
 } // namespace
 namespace yart {
-TraverseKernel lean_traverse_kernel(bool near, uint32_t max_stack, int ctas_per_sm); // device_trace_lean.cu
+TraverseKernel lean_traverse_kernel(bool near, uint32_t max_stack, int ctas_per_sm, bool compact); // device_trace_lean.cu
 }
 namespace {
 template <bool MIXED>
@@ -465,6 +506,9 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       T.nodes = m.nodes;
       T.tris = m.tris;
       T.leafgeo = m.leafgeo;
+      T.cnodes = m.cnodes;
+      T.cscale = m.cscale;
+      for (int k = 0; k < 3; ++k) T.corigin[k] = m.corigin[k];
       T.root = m.root;
       T.n_nodes = m.n_nodes;
       T.n_tris = m.n_tris;
@@ -491,7 +535,8 @@ int run_passes(yart_ctx* ctx, const QueryArgs& q, uint64_t* launches) {
       // YART_TUNE_LEAN_REF=1 forces it for both)
       static const int lean_ref = tune_env("YART_TUNE_LEAN_REF", 0);
       const bool use_lean = lean && mixed && !q.count && (q.near || lean_ref);
-      TraverseKernel k = use_lean ? yart::lean_traverse_kernel(q.near, (lean_stack24 || ctx->max_stack > 24) ? ctx->max_stack : 25u, lean)
+      TraverseKernel k = use_lean ? yart::lean_traverse_kernel(q.near, (lean_stack24 || ctx->max_stack > 24) ? ctx->max_stack : 25u, lean,
+                                                                 m.cnodes != nullptr && q.near)
                                   : pick_traverse_kernel(q.near, q.count, ctx->max_stack, mixed != 0);
       // occupancy query + carveout once per kernel variant (they cost tens of microseconds of host time,
       // which is the whole budget of a deep bounce)
@@ -800,6 +845,47 @@ static int set_scene_impl(yart_ctx* ctx, const yart_scene_desc* d) {
       k_pack_leaves<<<(q.n_nodes * 4u + 255u) / 256u, 256, 0, ctx->stream>>>(dn, q.n_nodes, dt, dl);
       CUDA_TRY(ctx, cudaGetLastError());
       meshes[i].leafgeo = reinterpret_cast<const float4*>(dl);
+    }
+    {
+      // Compact 64-byte nodes: an EXPERIMENT, off unless YART_TUNE_COMPACT=1 (2 = also for fine meshes).  It is
+      // bit-identical (tests/test_gpu_flags_and_abi.py runs the parity cases with it on) and cuts L1 wavefronts by 40 %,
+      // but costs ~55 % more instructions and loses ~20 % on the B200.  Eligible when inner node
+      // ids fit 27 bits, the bounding box is finite, and the 16-bit grid is fine against the mesh: the grid step is
+      // (largest extent) / 65534, and a mesh whose AVERAGE triangle is smaller than ~32 steps would send too many box
+      // tests to the exact fallback.  (Read per scene, not cached, so that one process can compare both.)
+      meshes[i].cnodes = nullptr;
+      meshes[i].cscale = 0.f;
+      for (int a = 0; a < 3; ++a) meshes[i].corigin[a] = 0.f;
+      const int compact = tune_env("YART_TUNE_COMPACT", 0);
+      double ext = 0.0;
+      bool finite = true;
+      for (int a = 0; a < 3; ++a) {
+        ext = std::fmax(ext, q.bbox_max[a] - q.bbox_min[a]);
+        finite = finite && std::isfinite(q.bbox_min[a]) && std::isfinite(q.bbox_max[a]) && std::fabs(q.bbox_min[a]) < 1e30 && std::fabs(q.bbox_max[a]) < 1e30;
+      }
+      if (compact && finite && ext > 0.0 && q.n_nodes < (1u << 27) && q.n_nodes > 0) {
+        int e = 0;
+        std::frexp(ext / 65534.0, &e); // ext / 65534 = m * 2^e with m in [0.5, 1): 2^e >= ext / 65534
+        const double step = std::ldexp(1.0, e);
+        const double avg_tri = ext / std::cbrt((double)std::max<uint32_t>(q.n_tris, 1u)); // a crude length scale of one triangle
+        if (e > -100 && e < 100 && (avg_tri / step >= 32.0 || compact > 1)) {
+          uint4* dc = nullptr;
+          CUDA_TRY(ctx, cudaMalloc((void**)&dc, (size_t)q.n_nodes * 64));
+          ctx->scene_allocs.push_back(dc);
+          // (the corner is the f32 image of the f64 bounding box's minimum, rounded DOWN so that every plane lies above it)
+          float org[3];
+          for (int a = 0; a < 3; ++a) {
+            float f = (float)q.bbox_min[a];
+            if ((double)f > q.bbox_min[a]) f = nextafterf(f, -INFINITY);
+            org[a] = f;
+          }
+          k_pack_nodes<<<(q.n_nodes + 255u) / 256u, 256, 0, ctx->stream>>>(dn, q.n_nodes, org[0], org[1], org[2], (float)step, dc);
+          CUDA_TRY(ctx, cudaGetLastError());
+          meshes[i].cnodes = dc;
+          meshes[i].cscale = (float)step;
+          for (int a = 0; a < 3; ++a) meshes[i].corigin[a] = org[a];
+        }
+      }
     }
     meshes[i].root = q.root;
     meshes[i].max_stack = q.max_stack;
