@@ -765,5 +765,16 @@ def main():
     return run_sweep(args) if args.workload == "sweep" else run_render(args)
 
 
+def _keep_stdout_for_the_json_line():
+    """Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner there at the first
+    communicator).  The contract is ONE JSON line on stdout: send everything else that lands on fd 1 to stderr and keep
+    the real stdout for Python's own prints, which in this script are the JSON lines only."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _keep_stdout_for_the_json_line()
     sys.exit(main())
