@@ -682,6 +682,21 @@ def run_sweep(args):
     rig.barrier()
     _, (ms2,) = rig.reduce_max_sum([0.0], [e0.elapsed_time(e1)])
     hit_rate = float((hits_np["prim_id"] != pkg.MISS).mean())
+    # the same through yart_closest_hit_f32: 24 B in + 16 B out per ray
+    h_r32 = torch.empty((hi - lo) * 24, dtype=torch.uint8).pin_memory()
+    h_h32 = torch.empty((hi - lo) * 16, dtype=torch.uint8).pin_memory()
+    r32_np = h_r32.numpy().view(pkg.abi.RAY_F32_DTYPE)
+    h32_np = h_h32.numpy().view(pkg.abi.HIT_F32_DTYPE)
+    r32_np["origin"], r32_np["direction"] = rays_np["origin"], rays_np["direction"]
+    ctx.closest_hit_f32(r32_np, 0, 0.0, float("inf"), pkg.ORDER_NEAR, hits=h32_np)
+    rig.barrier()
+    g0, g1 = rig.event(), rig.event()
+    g0.record(rig.stream)
+    for _ in range(K2):
+        ctx.closest_hit_f32(r32_np, 0, 0.0, float("inf"), pkg.ORDER_NEAR, hits=h32_np)
+    g1.record(rig.stream)
+    rig.barrier()
+    _, (ms3,) = rig.reduce_max_sum([0.0], [g0.elapsed_time(g1)])
 
     cpu_baseline = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
@@ -724,7 +739,11 @@ def run_sweep(args):
             "hit_rate": hit_rate,
             "e2e": {"value": n * K2 / ms2 / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": (hi - lo) * 48,
                     "d2h_bytes_per_step": (hi - lo) * 40, "steps": K2, "ms_per_step": ms2 / K2,
-                    "note": "pinned host ray / hit arrays through yart_closest_hit: PCIe-bound"},
+                    "note": "pinned host ray / hit arrays through yart_closest_hit, which pipelines upload / kernels / download in "
+                            "512 Ki-ray chunks: bound by the 805 MB upload over PCIe",
+                    "f32_records": {"value": n * K2 / ms3 / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": (hi - lo) * 24,
+                                    "d2h_bytes_per_step": (hi - lo) * 16, "ms_per_step": ms3 / K2,
+                                    "what": "the same rays and call shape through yart_closest_hit_f32"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_traverse<NEAR> (one launch per step) + k_export", "achieved": achieved, "peak": peak,

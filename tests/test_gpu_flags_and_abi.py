@@ -498,3 +498,28 @@ def test_compact_nodes_are_bit_identical(yart, orc, ctx, mesh_scene, name, monke
     finally:
         monkeypatch.delenv("YART_TUNE_COMPACT")
         ctx.set_scene(ms.desc)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-buffer queries run as a chunk pipeline (upload / kernels / download overlapped): same answers as one piece
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scene", ["cornell-box-smoke", "david"])
+def test_chunked_host_queries_equal_the_unchunked_ones(yart, ctx, scene, monkeypatch):
+    preset = yart.ScenePreset(scene, seed=1)
+    ctx.set_scene(preset)
+    cam = preset.camera(320, 240)
+    rays, _, _ = ctx.camera_rays(cam, 320, 240, 0, 3)          # 230,400 rays; the smoke scene draws random numbers per ray
+    monkeypatch.setenv("YART_TUNE_HOST_CHUNK", str(1 << 30))
+    whole, st_w = ctx.closest_hit(rays, yart.TARGET_WORLD, 0.001, INF, yart.ORDER_NEAR, count_visits=True)
+    monkeypatch.setenv("YART_TUNE_HOST_CHUNK", "4099")           # 57 ragged chunks
+    parts, st_p = ctx.closest_hit(rays, yart.TARGET_WORLD, 0.001, INF, yart.ORDER_NEAR, count_visits=True)
+    assert whole.tobytes() == parts.tobytes()
+    assert (st_p.rays, st_p.node_visits, st_p.tri_tests) == (st_w.rays, st_w.node_visits, st_w.tri_tests)
+    assert st_p.kernel_launches > st_w.kernel_launches
+    r32 = np.empty(len(rays), dtype=yart.abi.RAY_F32_DTYPE)
+    r32["origin"], r32["direction"] = rays["origin"], rays["direction"]
+    monkeypatch.setenv("YART_TUNE_HOST_CHUNK", str(1 << 30))
+    whole32, _ = ctx.closest_hit_f32(r32, yart.TARGET_WORLD, 0.001, INF, yart.ORDER_REFERENCE)
+    monkeypatch.setenv("YART_TUNE_HOST_CHUNK", "70001")
+    parts32, _ = ctx.closest_hit_f32(r32, yart.TARGET_WORLD, 0.001, INF, yart.ORDER_REFERENCE)
+    assert whole32.tobytes() == parts32.tobytes()

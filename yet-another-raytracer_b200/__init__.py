@@ -336,10 +336,14 @@ class Context:
         return hits, st
 
     def closest_hit_f32(self, rays, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"), order=ORDER_REFERENCE,
-                        count_visits=False):
-        """yart_closest_hit_f32 with host buffers: rays is an array of abi.RAY_F32_DTYPE."""
+                        count_visits=False, hits=None):
+        """yart_closest_hit_f32 with host buffers: rays is an array of abi.RAY_F32_DTYPE (hits: an optional caller-owned
+        output array, e.g. in pinned memory)."""
         rays = np.ascontiguousarray(rays, dtype=abi.RAY_F32_DTYPE)
-        hits = np.empty(rays.shape[0], dtype=abi.HIT_F32_DTYPE)
+        if hits is None:
+            hits = np.empty(rays.shape[0], dtype=abi.HIT_F32_DTYPE)
+        elif hits.dtype != abi.HIT_F32_DTYPE or hits.shape != (rays.shape[0],) or not hits.flags.c_contiguous:
+            raise ValueError("hits must be a contiguous abi.HIT_F32_DTYPE array as long as rays")
         st = abi.Stats()
         flags = FLAG_COUNT_VISITS if count_visits else 0
         self._check(_lib.yart_closest_hit_f32(self._h, target, rays.ctypes.data, rays.shape[0], t_min, t_max, order, flags,

@@ -371,6 +371,9 @@ struct yart_ctx {
   DevBuf rays, hits_export, time, wavelength, throughput, hits, queue_a, queue_b, counts, work, counters, film, rgba;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;
+  // host-buffer closest-hit queries: copy streams + events of the chunk pipeline (made on first use)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
 
   void free_scene() {
     for (void* p : scene_allocs) cudaFree(p);
@@ -646,6 +649,9 @@ void yart_ctx_destroy(yart_ctx* ctx) {
                     &ctx->queue_a, &ctx->queue_b, &ctx->counts, &ctx->work, &ctx->counters, &ctx->film, &ctx->rgba};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->d_cie) cudaFree(ctx->d_cie);
@@ -1059,21 +1065,19 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
   const size_t ray_bytes = f32 ? sizeof(yart_ray_f32) : sizeof(yart_ray), hit_bytes = f32 ? sizeof(yart_hit_f32) : sizeof(yart_hit);
   const bool dev = (flags & YART_FLAG_DEVICE_PTRS) != 0;
   const bool count = (flags & YART_FLAG_COUNT_VISITS) != 0;
-  const void* d_rays = rays;
-  void* d_hits = hits;
+  const char* d_rays = static_cast<const char*>(rays);
+  char* d_hits = static_cast<char*>(hits);
   if (!dev) {
     CUDA_TRY(ctx, ctx->rays.reserve(n * ray_bytes));
     CUDA_TRY(ctx, ctx->hits_export.reserve(n * hit_bytes));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rays.p, rays, n * ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    d_rays = ctx->rays.p;
-    d_hits = ctx->hits_export.p;
+    d_rays = ctx->rays.as<char>();
+    d_hits = ctx->hits_export.as<char>();
   }
   const uint32_t n_list = (target == YART_TARGET_WORLD) ? ctx->scene.n_objects : 1u;
   const size_t work_bytes = ((size_t)n_list + 2) * sizeof(uint32_t);
   CUDA_TRY(ctx, ctx->work.reserve(work_bytes));
   CUDA_TRY(ctx, ctx->counters.reserve(64));
   CUDA_TRY(ctx, ctx->hits.reserve(n * sizeof(DevHit)));
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->work.p, 0, work_bytes, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
 
   yart_object solo;
@@ -1082,11 +1086,6 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
   solo.cos_theta = 1.0;
   QueryArgs q;
   memset(&q, 0, sizeof(q));
-  if (f32) q.c.rays32 = reinterpret_cast<const yart_ray_f32*>(d_rays);
-  else q.c.rays = reinterpret_cast<const yart_ray*>(d_rays);
-  q.c.n_items = n;
-  q.c.n_rays = (uint32_t)n;
-  q.c.hits = ctx->hits.as<DevHit>();
   q.c.t_min = t_min;
   q.c.t_max = t_max;
   DevScene export_scene = ctx->scene;
@@ -1109,19 +1108,85 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
   q.near = order == YART_ORDER_NEAR;
   q.count = count;
   uint64_t launches = 0;
+  // The passes + the export over rays [off, off + len), on the context's stream.
+  auto run_range = [&](uint64_t off, uint64_t len) -> int {
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->work.p, 0, work_bytes, ctx->stream));
+    const char* r = d_rays + off * ray_bytes;
+    q.c.rays = f32 ? nullptr : reinterpret_cast<const yart_ray*>(r);
+    q.c.rays32 = f32 ? reinterpret_cast<const yart_ray_f32*>(r) : nullptr;
+    q.c.n_items = len;
+    q.c.n_rays = (uint32_t)len;
+    q.c.hits = ctx->hits.as<DevHit>() + off;
+    q.pixel_base = (uint32_t)off; // (keeps a ray's Philox stream = its index in the caller's array)
+    const int rc = run_passes(ctx, q, &launches);
+    if (rc) return rc;
+    if (f32)
+      k_export_f32<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, export_scene.objects, q.c.hits,
+                                                               reinterpret_cast<yart_hit_f32*>(d_hits + off * hit_bytes), len);
+    else
+      k_export<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, q.c.rays, q.c.hits,
+                                                           reinterpret_cast<yart_hit*>(d_hits + off * hit_bytes), len);
+    launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return YART_OK;
+  };
+  // Host buffers: the arrays go through in chunks, the upload of chunk i+1 and the download of chunk i-1 overlapping the
+  // kernels of chunk i on two copy streams (PCIe is full duplex; the transfers, not the traversal, bound this call:
+  // 88 B per ray against ~1.5 ns of kernel time).  With pageable host memory the copies block the calling thread, so
+  // the kernels of a chunk are queued BEFORE the next upload is issued; with pinned memory everything is asynchronous.
+  const int chunk_env = tune_env("YART_TUNE_HOST_CHUNK", 1 << 19); // (rays per chunk, read per call; 2^19 measured best: tools/host_chunk_probe.py)
+  const uint64_t chunk = dev ? n : (uint64_t)std::max(chunk_env, 1024);
+  const uint64_t n_chunks = (n + chunk - 1) / chunk;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = run_passes(ctx, q, &launches);
-  if (rc) return rc;
-  if (f32)
-    k_export_f32<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, export_scene.objects, ctx->hits.as<DevHit>(),
-                                                             reinterpret_cast<yart_hit_f32*>(d_hits), n);
-  else
-    k_export<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(export_scene, reinterpret_cast<const yart_ray*>(d_rays), ctx->hits.as<DevHit>(),
-                                                         reinterpret_cast<yart_hit*>(d_hits), n);
-  launches++;
-  CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(hits, d_hits, n * hit_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dev || n_chunks == 1) {
+    if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rays.p, rays, n * ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = run_range(0, n);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(hits, d_hits, n * hit_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    if (!ctx->copy_in) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    if (!ctx->copy_out) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    while (ctx->chunk_events.size() < 2 * n_chunks + 1) {
+      cudaEvent_t e;
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->chunk_events.push_back(e);
+    }
+    cudaEvent_t* up = ctx->chunk_events.data();              // up[i]: chunk i is on the device
+    cudaEvent_t* done = ctx->chunk_events.data() + n_chunks; // done[i]: chunk i's hits are exported
+    cudaEvent_t start = ctx->chunk_events[2 * n_chunks];
+    // (the device buffers may still be read by earlier work on the context's stream)
+    CUDA_TRY(ctx, cudaEventRecord(start, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, start, 0));
+    auto upload_chunk = [&](uint64_t i) -> int {
+      const uint64_t off = i * chunk, len = std::min(chunk, n - off);
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rays.as<char>() + off * ray_bytes, static_cast<const char*>(rays) + off * ray_bytes,
+                                    len * ray_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+      CUDA_TRY(ctx, cudaEventRecord(up[i], ctx->copy_in));
+      return YART_OK;
+    };
+    int rc = upload_chunk(0);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n_chunks; ++i) {
+      const uint64_t off = i * chunk, len = std::min(chunk, n - off);
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, up[i], 0));
+      if ((rc = run_range(off, len)) != YART_OK) break;
+      CUDA_TRY(ctx, cudaEventRecord(done[i], ctx->stream));
+      if (i + 1 < n_chunks && (rc = upload_chunk(i + 1)) != YART_OK) break;
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, done[i], 0));
+      CUDA_TRY(ctx, cudaMemcpyAsync(static_cast<char*>(hits) + off * hit_bytes, d_hits + off * hit_bytes, len * hit_bytes,
+                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    // nothing of this call may outlive it, error or not
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaError_t ce = cudaStreamSynchronize(ctx->copy_out);
+    if (rc) {
+      cudaStreamSynchronize(ctx->stream);
+      return rc;
+    }
+    CUDA_TRY(ctx, ce);
+  }
   unsigned long long c[2] = {0, 0};
   if (count) CUDA_TRY(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1132,7 +1197,7 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
     stats->node_visits = c[0];
     stats->tri_tests = c[1];
     stats->kernel_launches = launches;
-    stats->trace_launches = (uint32_t)(launches - 1);
+    stats->trace_launches = (uint32_t)(launches - (dev ? 1 : n_chunks)); // (one export kernel per chunk)
     stats->gpu_ms = ms;
     stats->trace_ms = ms;
   }
