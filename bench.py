@@ -67,9 +67,13 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  One sample per second:
-    on some boxes every nvidia-smi query stalls the GPU for a few ms, and at 5 Hz that showed up as ~1.5 % of a step."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """SM clock + clock-event (throttle) reasons during the timed region, one sample per second (B200_PROFILING.md's
+    clocks line).  Read through NVML inside this process (pynvml: two light queries per sample); a spawned
+    `nvidia-smi --query-gpu=... -lms` is the fallback.  Why not nvidia-smi first: on some boxes each of its queries (it
+    also read power.draw) held a driver lock long enough to stall this launch-heavy step -- 1.5 % of a step at 5 Hz on
+    one box, 11 % at 1 Hz on another, while the untimed-by-sampler e2e leg of the same run was unaffected."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -77,41 +81,91 @@ class ClockSampler:
         self.idx = device_index
         self.proc = None
         self.lines = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.handle = None
+        self.how = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+            phys = int(vis[self.idx]) if self.idx < len(vis) else self.idx
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
 
     def start(self):
+        try:
+            self.nv, self.handle = self._nvml_handle()
+            self._sample_nvml()  # (fails here, not in the thread, if a query is unsupported)
+            self.sm, self.mx = [], []
+            self.how = "nvml"
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.handle = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "1000"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _sample_nvml(self):
+        nv, h = self.nv, self.handle
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(h))
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            self._stop.wait(1.0)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        if self.handle is not None:
+            self._stop.set()
+            self._thread.join(timeout=2.0)
+        elif self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    self.sm.append(float(f[1]))
+                    self.mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for (name, _), v in zip(self.REASONS, f[4:8]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
+        sm, mx = self.sm, self.mx
         busy = [x for x in sm if x > 0.5 * max(mx + [1.0])] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.how}
 
 
 def profiled_traffic():
