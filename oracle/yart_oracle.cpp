@@ -377,6 +377,10 @@ struct Counters {
 
 // L4QBVH::hit (qbvh.rs:381-543).  NEAR=false is the reference verbatim.  NEAR=true is the
 // mirrored order with mirrored tie rules (yart.h YART_ORDER_NEAR) and must return the same hit.
+// The mirrored rules are non-strict (`t_max >= t`: the LAST equal-t hit found wins, which is the
+// reference's first), so NEAR starts one step below the t_max it is given: against the caller's bound
+// and the hits of earlier objects the reference is strict (`t_max > t`, `tfar > tnear` with
+// tfar <= t_max), and a hit or box entry AT that bound must stay out.
 template <bool NEAR>
 MeshHit qbvh_hit(const Mesh& m, const Ray& ray, double t_min, double t_max_in, Counters* cnt) {
   MeshHit best;
@@ -390,7 +394,7 @@ MeshHit qbvh_hit(const Mesh& m, const Ray& ray, double t_min, double t_max_in, C
   const double ro[3] = {ray.o.x, ray.o.y, ray.o.z};
   const double rd[3] = {ray.d.x, ray.d.y, ray.d.z};
   const double inv[3] = {1.0 / rd[0], 1.0 / rd[1], 1.0 / rd[2]};
-  double t_max = t_max_in;
+  double t_max = NEAR ? std::nextafter(t_max_in, -kInf) : t_max_in;
   size_t max_cursor = 0;
 
   for (;;) {

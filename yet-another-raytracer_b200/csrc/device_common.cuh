@@ -42,6 +42,17 @@ YART_DEV D3 cross(D3 a, D3 b) {
   return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 YART_DEV double length_squared(D3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+// The largest double strictly below x (x = -inf and NaN stay).  NEAR-order traversal starts from just_below(t_max): its
+// tests are non-strict (`t <= t_best`, `t_best >= t_near`: the mirrored tie rule needs that among THIS mesh's equal-t
+// hits), and starting one step below makes them strict against what the caller / the earlier objects left -- which
+// is what the reference's `t_max > t` (qbvh.rs:478) and `tfar > tnear` with tfar <= t_max (qbvh.rs:495-532) are.
+YART_DEV double just_below(double x) {
+  if (!(x > -d_inf())) return x;
+  if (x == 0.0) return __longlong_as_double((long long)0x8000000000000001ull);
+  const long long b = __double_as_longlong(x);
+  return __longlong_as_double(b + (b < 0 ? 1 : -1));
+}
+
 YART_DEV double length(D3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
 YART_DEV D3 unit_vector(D3 a) {
   double l = length(a);

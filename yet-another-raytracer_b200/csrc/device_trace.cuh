@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
   double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0; // ray in the mesh's space
   uint32_t sgn = 0;  // ORDER_TABLE sign bits (mirrored when NEAR)
   uint32_t pos = 0;  // bit a set: direction component a is >= 0 (qbvh.rs:388-392); bit 3: `weird`
-  double t_best = 0, t_entry = 0, best_bu = 0, best_bv = 0;
+  double t_best = 0, best_bu = 0, best_bv = 0;
   uint32_t best_prim = YART_MISS; // YART_MISS = this mesh has not produced a hit
   bool exhausted = false;         // the global queue is empty
   unsigned long long n_nodes = 0, n_tris = 0, n_exact = 0;
@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           if (P.c.rays32) load_ray_f32(P.c.rays32 + ray_id, ro, rd);
           else load_ray(P.c.rays + ray_id, ro, rd);
           t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
+          if (NEAR) t_best = just_below(t_best); // strict against earlier objects / the caller's t_max (device_common.cuh)
           // ray into the instance's space (hittable.rs:137-143, 218-227); uniform across the launch
           if (P.wrap & YART_WRAP_TRANSLATE) ro = ro - d3(P.offset[0], P.offset[1], P.offset[2]);
           if (P.wrap & YART_WRAP_ROTATE_Y) {
@@ -539,7 +540,6 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
           }
           cur = P.root;
           sp = 0;
-          t_entry = t_best;
           best_prim = YART_MISS;
           best_bu = best_bv = 0.0;
         }
@@ -683,8 +683,8 @@ __global__ void __launch_bounds__(kTraceThreads, YART_TRAVERSE_MIN_BLOCKS) k_tra
     const double t = f * (e2x * qx + e2y * qy + e2z * qz);                                                          \
     ok = ok && (t >= t_min);                                                                                        \
     /* REFERENCE: first found wins (`t_max > t`, qbvh.rs:478).  NEAR: mirrored -- last found wins among this */    \
-    /* mesh's equal-t hits, still strictly closer than what earlier objects left.                            */    \
-    ok = ok && (NEAR ? ((t <= t_best) && (t < t_entry)) : (t_best > t));                                            \
+    /* mesh's equal-t hits; strictness against earlier objects comes from the start value just_below(t_max).  */    \
+    ok = ok && (NEAR ? (t <= t_best) : (t_best > t));                                                               \
     if (ok) {                                                                                                       \
       t_best = t; best_prim = first + (I_); best_bu = u; best_bv = v;                                               \
       if (MIXED) t_best_f = (float)t;                                                                               \

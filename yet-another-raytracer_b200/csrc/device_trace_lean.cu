@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
   __shared__ uint32_t s_stack[STACK + 1][kTraceThreads];
   // what only the exact f64 code needs lives in shared memory, one column per lane: the ray in the mesh's space
   // (o, d), the interval's upper end on entry, and the barycentrics of the best hit
-  __shared__ double s_ray[7][kTraceThreads];
+  __shared__ double s_ray[6][kTraceThreads];
   __shared__ double s_buv[2][kTraceThreads];
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31;
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
           if (P.c.rays32) load_ray_f32(P.c.rays32 + ray_id, ro, rd);
           else load_ray(P.c.rays + ray_id, ro, rd);
           t_best = P.c.first_pass ? P.c.t_max : fmin(P.c.hits[ray_id].t, P.c.t_max);
+          if (NEAR) t_best = just_below(t_best); // strict against earlier objects / the caller's t_max (device_common.cuh)
           // ray into the instance's space (hittable.rs:137-143, 218-227); uniform across the launch
           if (P.wrap & YART_WRAP_TRANSLATE) ro = ro - d3(P.offset[0], P.offset[1], P.offset[2]);
           if (P.wrap & YART_WRAP_ROTATE_Y) {
@@ -201,7 +202,6 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
           const double ix = 1.0 / dx, iy = 1.0 / dy, iz = 1.0 / dz; // qbvh.rs:403-407
           s_ray[0][tid] = ox; s_ray[1][tid] = oy; s_ray[2][tid] = oz;
           s_ray[3][tid] = dx; s_ray[4][tid] = dy; s_ray[5][tid] = dz;
-          s_ray[6][tid] = t_best; // t_entry
           pos = (dx >= 0.0 ? 1u : 0u) | (dy >= 0.0 ? 2u : 0u) | (dz >= 0.0 ? 4u : 0u); // qbvh.rs:388-392
           sgn = NEAR ? (pos ^ 7u) : pos;
           // (b - o) * (1/d) can only be NaN when 1/d is infinite or the ray itself is not finite
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
       const uint32_t first = cur & 0x7FFFFFFu;
       YART_CHECK(count >= 1 && count <= 4 && first + count <= P.n_tris);
       const double ox = s_ray[0][tid], oy = s_ray[1][tid], oz = s_ray[2][tid];
-      const double dx = s_ray[3][tid], dy = s_ray[4][tid], dz = s_ray[5][tid], t_entry = s_ray[6][tid];
+      const double dx = s_ray[3][tid], dy = s_ray[4][tid], dz = s_ray[5][tid];
       // Moeller-Trumbore exactly as qbvh.rs:419-489 on one triangle given as 9 floats
 #define YART_TRI_TEST(I_, F0, F1, F2, F3, F4, F5, F6, F7, F8)                                                       \
   {                                                                                                                 \
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
     ok = ok && (t >= t_min);                                                                                        \
     /* REFERENCE: first found wins (`t_max > t`, qbvh.rs:478).  NEAR: mirrored -- last found wins among this */    \
     /* mesh's equal-t hits, still strictly closer than what earlier objects left.                            */    \
-    ok = ok && (NEAR ? ((t <= t_best) && (t < t_entry)) : (t_best > t));                                            \
+    ok = ok && (NEAR ? (t <= t_best) : (t_best > t));                                                               \
     if (ok) {                                                                                                       \
       t_best = t; best_prim = first + (I_); s_buv[0][tid] = u; s_buv[1][tid] = v;                                   \
       if (MIXED) t_best_f = (float)t;                                                                               \
