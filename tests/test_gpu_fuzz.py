@@ -82,3 +82,28 @@ def test_coincident_meshes_first_in_list_order_wins(yart, orc, ctx):
         for count in (False, True):
             got, _ = ctx.closest_hit(rays, yart.TARGET_WORLD, 0.001, INF, order, count_visits=count)
             assert got.tobytes() == want.tobytes(), (order, count)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scene_sampling_flags_and_f32_records(yart, orc, ctx, seed):
+    sc = FuzzScene(yart, 3000 + seed)
+    s = orc.Scene(sc)
+    ctx.set_scene(sc.desc)
+    w, h, spp, depth = 40, 32, 6, 10
+    cam = sc.camera(w, h)
+    flags = yart.FLAG_UNBIASED_LIGHT_PICK | yart.FLAG_RUSSIAN_ROULETTE | yart.FLAG_DEPTH_ZERO_BLACK
+    want, _ = s.render(cam, w, h, 0, spp, max_depth=depth, seed=9, n_threads=os.cpu_count(), flags=flags)
+    got, _ = ctx.render(cam, w, h, 0, spp, max_depth=depth, seed=9, flags=flags)
+    compare_films(got, want, "fuzz scene %d with all sampling flags" % seed, 0.93)
+    # f32 records: the f64 query on the widened rays, rounded
+    o, d = sc.rays(30000)
+    r32 = np.empty(len(o), dtype=yart.abi.RAY_F32_DTYPE)
+    r32["origin"], r32["direction"] = o.astype(np.float32), d.astype(np.float32)
+    r64 = yart.make_rays(r32["origin"].astype(np.float64), r32["direction"].astype(np.float64))
+    t_min = 2.0 ** -10  # (a float: the f32 entry point takes t_min as one, and a medium's entry clamp shows the difference)
+    ref, _ = ctx.closest_hit(r64, yart.TARGET_WORLD, t_min, INF, yart.ORDER_NEAR)
+    got32, _ = ctx.closest_hit_f32(r32, yart.TARGET_WORLD, t_min, INF, yart.ORDER_NEAR)
+    assert np.array_equal(got32["prim_id"], ref["prim_id"])
+    hit = ref["prim_id"] != yart.MISS
+    for f in ("t", "u", "v"):
+        assert np.array_equal(got32[f][hit], ref[f][hit].astype(np.float32)), f
