@@ -222,7 +222,13 @@ typedef struct yart_hit_f32 {
  *  REFERENCE: exactly qbvh.rs:14-31,521-533 -- the ORDER_TABLE lookup, which visits the FAR
  *    child first; first-found wins among equal-t hits (qbvh.rs:478).
  *  NEAR: the mirrored table (near child first, ~30% fewer node visits) with mirrored tie
- *    rules (last-found wins, lanes reversed), which yields the same hit as REFERENCE.   */
+ *    rules (last-found wins, lanes reversed; strict against the t_max it is given).  It yields the
+ *    same hit as REFERENCE on every ray of the parity sets (16 Mi random / axis / path rays per
+ *    mesh, all presets).  The one known exception is a measure-zero set: a ray that passes within
+ *    rounding of a vertex or edge lying ON a node's box face, where the slab value and the
+ *    Moller-Trumbore t disagree in the last bit -- each order then culls the box the other enters
+ *    and returns another member of the same near-tie set (|dt| <= a few ulp; tests/test_gpu_fuzz.py
+ *    aims rays at such points and bounds it).  REFERENCE is exact always.                */
 enum { YART_ORDER_REFERENCE = 0, YART_ORDER_NEAR = 1 };
 
 /* flags of yart_closest_hit / yart_render */

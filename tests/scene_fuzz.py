@@ -257,3 +257,61 @@ class FuzzScene:
         d[:k] = 0.0
         d[np.arange(k), axis] = r.choice([-1.0, 1.0], size=k) * r.uniform(0.5, 3, size=k)
         return o, d
+
+
+def fuzz_soup(seed, n_tris):
+    """A random triangle soup (positions f32, normals f64, uvs f32) with the awkward cases mixed in: lattice vertices
+    (equal centroids, exact ties, flat boxes), degenerate and sliver triangles, axis-aligned triangles, duplicated
+    triangles, far-away clusters and signed zeros."""
+    r = np.random.default_rng(seed)
+    style = seed % 4
+    if style == 0:
+        pos = r.uniform(-10, 10, size=(n_tris, 1, 3)) + r.uniform(-1.5, 1.5, size=(n_tris, 3, 3))
+    elif style == 1:
+        pos = r.integers(-4, 5, size=(n_tris, 3, 3)).astype(np.float64)
+    elif style == 2:
+        pos = r.uniform(-3, 3, size=(n_tris, 1, 3)) + r.uniform(-0.4, 0.4, size=(n_tris, 3, 3))
+        far = r.random(n_tris) < 0.2
+        pos[far] += np.array([4096.0, -2048.0, 1e4])
+    else:
+        pos = r.uniform(-6, 6, size=(n_tris, 1, 3)) + r.uniform(-2, 2, size=(n_tris, 3, 3))
+        flat = r.random(n_tris) < 0.3                       # axis-aligned: one coordinate shared by the three vertices
+        ax = r.integers(0, 3, size=n_tris)
+        idx = np.flatnonzero(flat)
+        pos[idx, :, ax[idx]] = np.round(pos[idx, 0, ax[idx]])[:, None]
+    k = max(1, n_tris // 12)
+    deg = r.choice(n_tris, size=k, replace=False)
+    pos[deg, 2] = pos[deg, 1]                                # degenerate: two equal vertices
+    dup = r.choice(n_tris, size=k, replace=False)
+    pos[dup] = pos[r.choice(n_tris, size=k)]                 # exact duplicates (ties between different triangles)
+    pos[r.random(pos.shape) < 0.02] = -0.0
+    pos = pos.astype(np.float32)
+    nrm = r.standard_normal((n_tris, 3, 3))
+    uv = r.random((n_tris, 3, 2)).astype(np.float32)
+    return pos, nrm, uv
+
+
+def fuzz_mesh_rays(seed, pos, n):
+    """Rays for a soup: random ones, rays through vertices and edge midpoints (ties), axis-parallel rays (zero
+    components: NaN slabs), rays starting ON a vertex, denormal and huge direction components."""
+    r = np.random.default_rng(seed + 77)
+    p = pos.astype(np.float64)
+    lo, hi = p.reshape(-1, 3).min(0), p.reshape(-1, 3).max(0)
+    span = np.maximum(hi - lo, 1.0)
+    o = r.uniform(lo - 0.5 * span, hi + 0.5 * span, size=(n, 3))
+    d = r.standard_normal((n, 3)) * r.uniform(0.01, 20, size=(n, 1))
+    q = n // 6
+    tri = r.integers(0, len(p), size=3 * q)
+    vert = p[tri, r.integers(0, 3, size=3 * q)]
+    d[:q] = (vert[:q] - o[:q]) * r.choice([0.5, 1.0, 2.0], size=(q, 1))                    # through a vertex
+    mid = 0.5 * (p[tri[q:2 * q], 0] + p[tri[q:2 * q], 1])
+    d[q:2 * q] = mid - o[q:2 * q]                                                          # through an edge midpoint
+    o[2 * q:3 * q] = vert[2 * q:3 * q]                                                     # starting on a vertex
+    a = r.integers(0, 3, size=q)
+    d[3 * q:4 * q] = 0.0
+    d[np.arange(3 * q, 4 * q), a] = r.choice([-1.0, 1.0, 3.5], size=q)                     # axis-parallel
+    o[3 * q:4 * q] = vert[:q] + 0.0
+    o[np.arange(3 * q, 4 * q), a] -= 5.0 * np.sign(d[np.arange(3 * q, 4 * q), a])
+    w = slice(4 * q, 4 * q + q // 2)
+    d[w, r.integers(0, 3)] = r.choice([5e-324, -1e-310, 1e-200, 1e200], size=q // 2)       # denormal / huge components
+    return o, d

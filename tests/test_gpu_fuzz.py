@@ -107,3 +107,50 @@ def test_random_scene_sampling_flags_and_f32_records(yart, orc, ctx, seed):
     hit = ref["prim_id"] != yart.MISS
     for f in ("t", "u", "v"):
         assert np.array_equal(got32[f][hit], ref[f][hit].astype(np.float32)), f
+
+
+@pytest.mark.parametrize("seed,n_tris", [(s, n) for s, n in enumerate([5, 6, 7, 8, 9, 12, 13, 16, 17, 31, 33, 64, 100, 257, 1000, 3001, 20000, 4, 11, 500])])
+@pytest.mark.parametrize("compact", [0, 2])
+def test_random_soup_build_and_closest_hit(yart, orc, ctx, seed, n_tris, compact, monkeypatch):
+    """Random triangle soups: device-built tree == host-built tree byte for byte, and L4QBVH::hit bit-exact against the
+    oracle (both orders, with and without visit counting, two [t_min, t_max] windows)."""
+    from scene_fuzz import fuzz_soup, fuzz_mesh_rays
+    from test_gpu_build import assert_same_tree
+    pos, nrm, uv = fuzz_soup(seed, n_tris)
+    t, keep = yart.trimesh_from_arrays(pos, nrm, uv)
+    if n_tris <= 4:  # L4QBVH::new yields no nodes (SURVEY A-17): refused by both builders
+        with pytest.raises(yart.YartError):
+            yart.L4QBVH(t, keepalive=keep, ctx=ctx)
+        with pytest.raises(yart.YartError):
+            yart.L4QBVH(t, keepalive=keep)
+        return
+    assert_same_tree(yart, ctx, t, keep)
+    ms = orc.MeshScene(pos, nrm, uv)
+    s = orc.Scene(ms)
+    monkeypatch.setenv("YART_TUNE_COMPACT", str(compact))  # 2: the compact-node experiment, on whatever the grid is like
+    ctx.set_scene(ms.desc)
+    o, d = fuzz_mesh_rays(seed, pos, 40000)
+    rays = yart.make_rays(o, d)
+    for t_min, t_max in ((0.001, INF), (0.0, 2.0)):
+        wants = {}
+        for order in (yart.ORDER_REFERENCE, yart.ORDER_NEAR):
+            want, cnt = wants[order] = s.closest_hit(rays, 0, t_min, t_max, order, n_threads=os.cpu_count())
+            for count in (False, True):
+                got, st = ctx.closest_hit(rays, 0, t_min, t_max, order, count_visits=count)
+                for f in ("t", "u", "v", "prim_id"):
+                    same = (got[f] == want[f]) | ((got[f] != got[f]) & (want[f] != want[f]))
+                    bad = np.flatnonzero(~same)
+                    assert bad.size == 0, "soup %d (%d tris) order %d count %s window (%g, %g) field %s: %d rays differ, first %d: ray %r gpu %r oracle %r" % (
+                        seed, n_tris, order, count, t_min, t_max, f, bad.size, bad[0], rays[bad[0]], got[bad[0]], want[bad[0]])
+                if count:
+                    assert (st.node_visits, st.tri_tests) == (cnt.node_visits, cnt.tri_tests), order
+        # Near-first against the reference order (yart.h, YART_ORDER_NEAR): identical except where a ray passes within
+        # rounding of a vertex / edge that lies ON a box face -- there each order culls the box the other one enters, and
+        # the two answers are members of the same near-tie set.  These soups aim a third of their rays at such points.
+        ref, near = wants[yart.ORDER_REFERENCE][0], wants[yart.ORDER_NEAR][0]
+        diff = np.flatnonzero((ref["t"] != near["t"]) | (ref["prim_id"] != near["prim_id"]))
+        assert diff.size <= 0.002 * len(rays)
+        assert ((ref["prim_id"][diff] != yart.MISS) & (near["prim_id"][diff] != yart.MISS)).all()
+        if t_min > 0.0:  # (with t_min = 0 the soups' degenerate triangles give spurious t = +-0 "hits" in the reference's
+            #             Moller-Trumbore, and which order meets them first is arbitrary -- both sides still agree bit for bit above)
+            assert (np.abs(ref["t"][diff] - near["t"][diff]) <= 1e-12 * np.abs(ref["t"][diff])).all()
