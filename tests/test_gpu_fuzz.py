@@ -154,3 +154,19 @@ def test_random_soup_build_and_closest_hit(yart, orc, ctx, seed, n_tris, compact
         if t_min > 0.0:  # (with t_min = 0 the soups' degenerate triangles give spurious t = +-0 "hits" in the reference's
             #             Moller-Trumbore, and which order meets them first is arbitrary -- both sides still agree bit for bit above)
             assert (np.abs(ref["t"][diff] - near["t"][diff]) <= 1e-12 * np.abs(ref["t"][diff])).all()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_film_finalize_on_random_films_with_special_values(yart, orc, ctx, seed):
+    """yart_film_finalize (main.rs:710-718, color.rs:92-107) on films with NaN, +-inf, negatives, zeros, huge and tiny
+    values, widths that are / are not multiples of 8, several spp."""
+    g = np.random.default_rng(seed)
+    h, w = int(g.integers(8, 50)), int(g.integers(8, 70))
+    film = g.random((h, w, 3)) * float(g.choice([0.01, 1.0, 30.0, 1e6]))
+    special = g.random((h, w, 3)) < 0.05
+    film[special] = g.choice([np.nan, np.inf, -np.inf, -1.0, 0.0, -0.0, 1e300, 1e-300, 5e-324], size=int(special.sum()))
+    spp = int(g.choice([1, 3, 64, 1024]))
+    a = ctx.film_finalize(film, spp)
+    b = orc.film_finalize(film, spp)
+    # pow() may differ in the last bit; a u8 can flip only when 256 * c sits within 1e-13 of an integer
+    assert (a != b).sum() <= 1, np.argwhere(a != b)[:5]
