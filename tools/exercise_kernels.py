@@ -49,4 +49,36 @@ comm.film_reduce(film, 48, 32, 0)
 comm.close()
 assert ctx.film_read(film, 48, 32).sum() > 0
 ctx.film_destroy(film)
+# random scene descriptions and triangle soups (tests/scene_fuzz.py): wrappers, groups, media, degenerate triangles
+from scene_fuzz import FuzzScene, fuzz_soup, fuzz_mesh_rays
+import ctypes as C
+
+
+def soup_scene(pos, nrm, uv):
+    abi = y.abi
+    tm, keep = y.trimesh_from_arrays(pos, nrm, uv)
+    tex, mat, obj, sd = abi.Texture(), abi.Material(), abi.Object(), abi.SceneDesc()
+    tex.kind, mat.kind = abi.TEX_SOLID, abi.MAT_LAMBERTIAN
+    obj.kind, obj.cos_theta = abi.OBJ_MESH, 1.0
+    sd.objects, sd.n_objects = C.pointer(obj), 1
+    sd.meshes, sd.n_meshes = C.pointer(tm), 1
+    sd.materials, sd.n_materials = C.pointer(mat), 1
+    sd.textures, sd.n_textures = C.pointer(tex), 1
+    return C.pointer(sd), (tm, keep, tex, mat, obj, sd)
+
+
+for seed in range(6):
+    sc = FuzzScene(y, 4000 + seed)
+    ctx.set_scene(sc.desc)
+    o, d = sc.rays(20000)
+    for order in (0, 1):
+        ctx.closest_hit(y.make_rays(o, d), y.TARGET_WORLD, 0.001, float("inf"), order, count_visits=bool(order))
+    ctx.render(sc.camera(32, 24), 32, 24, 0, 3, 12, 1, flags=flags if seed % 2 else 0)
+for seed, n_tris in ((1, 6), (2, 33), (3, 1000)):
+    pos, nrm, uv = fuzz_soup(seed, n_tris)
+    desc, keep = soup_scene(pos, nrm, uv)
+    ctx.set_scene(desc)
+    o, d = fuzz_mesh_rays(seed, pos, 20000)
+    for order in (0, 1):
+        ctx.closest_hit(y.make_rays(o, d), 0, 0.0, float("inf"), order)
 print("exercise done")
