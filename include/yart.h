@@ -373,8 +373,8 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* scene);
  * Host arrays go through in chunks of 2^19 rays, the upload of one chunk and the download of another overlapping the
  * kernels of a third on separate copy streams; page-locked (cudaHostAlloc / cudaHostRegister) arrays make that fully
  * asynchronous -- 0.92 Grays/s (f64 records) / 2.0 Grays/s (f32 records) end to end on a B200 behind PCIe 5, against
- * 0.52 / 0.99 unpipelined.  The call returns when `hits` is complete either way; stats->gpu_ms then spans the
- * whole pipeline. */
+ * 0.52 / 0.99 unpipelined.  The call returns when `hits` is complete either way; stats->gpu_ms is the time of
+ * the kernels alone (summed over the chunks), as with device arrays. */
 int yart_closest_hit(yart_ctx* ctx, uint32_t target, const yart_ray* rays, uint64_t n,
                      double t_min, double t_max, uint32_t order, uint32_t flags,
                      yart_hit* hits, yart_stats* stats /* may be NULL */);

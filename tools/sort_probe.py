@@ -1,16 +1,16 @@
 #!/usr/bin/env python3
 """How much would ray sorting buy?  Same 8 Mi random rays: unsorted vs sorted by direction octant, vs sorted by
 (octant, Morton code of the origin)."""
-import importlib, sys
+import importlib, os, sys
 from pathlib import Path
 import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import raysets
-from oracle import orc
+os.environ.setdefault("YART_TUNE_HOST_CHUNK", str(1 << 30))  # one launch per query (no host-array chunk pipeline)
 y = importlib.import_module("yet-another-raytracer_b200")
-m = y.TriangleMesh.from_obj(y.assets_dir() + "/david.obj")
-ms = orc.MeshScene(m.positions(), m.normals(), m.uvs()); q = y.L4QBVH.from_mesh(m)
+from bench import MeshOnlyScene
+ms = MeshOnlyScene(y, "david"); q = y.L4QBVH.from_mesh(ms.mesh)
 ctx = y.Context(0); ctx.set_scene(ms.desc)
 n = 1 << 23
 o, d = raysets.uniform(n, q.info.bbox_min, q.info.bbox_max)
@@ -22,7 +22,7 @@ def spread(v):
     v = (v | (v << 4)) & np.uint64(0x030C30C3); v = (v | (v << 2)) & np.uint64(0x09249249); return v
 morton = spread(cell[:, 0]) | (spread(cell[:, 1]) << np.uint64(1)) | (spread(cell[:, 2]) << np.uint64(2))
 def run(tag, idx):
-    rays = orc.abi.make_rays(o[idx], d[idx])
+    rays = y.make_rays(o[idx], d[idx])
     best = min(ctx.closest_hit(rays, 0, 0.0, float("inf"), y.ORDER_NEAR)[1].gpu_ms for _ in range(3))
     print("%-34s %.3f ms  %.0f Mrays/s" % (tag, best, n / best / 1e3), flush=True)
 run("unsorted", np.arange(n))

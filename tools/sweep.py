@@ -3,6 +3,7 @@
 library's own CUDA events.  Usage: python tools/sweep.py [--n 16777216] [--mesh david] [--reps 5]"""
 import argparse
 import importlib
+import os
 import sys
 import time
 from pathlib import Path
@@ -23,17 +24,18 @@ def main():
     ap.add_argument("--sets", default="uniform,axis")
     ap.add_argument("--count", action="store_true")
     a = ap.parse_args()
+    # one launch over the whole ray set (the library would otherwise pipeline host arrays in 2^19-ray chunks)
+    os.environ.setdefault("YART_TUNE_HOST_CHUNK", str(1 << 30))
     y = importlib.import_module("yet-another-raytracer_b200")
-    from oracle import orc
-    m = y.TriangleMesh.from_obj(y.assets_dir() + "/%s.obj" % a.mesh)
-    ms = orc.MeshScene(m.positions(), m.normals(), m.uvs())
-    q = y.L4QBVH.from_mesh(m)
+    from bench import MeshOnlyScene
+    ms = MeshOnlyScene(y, a.mesh)
+    q = y.L4QBVH.from_mesh(ms.mesh)
     ctx = y.Context(0)
     ctx.set_scene(ms.desc)
     for rs in a.sets.split(","):
         gen = raysets.uniform if rs == "uniform" else raysets.axis
         o, d = gen(a.n, q.info.bbox_min, q.info.bbox_max)
-        rays = orc.abi.make_rays(o, d)
+        rays = y.make_rays(o, d)
         for order, oname in ((y.ORDER_REFERENCE, "reference"), (y.ORDER_NEAR, "near")):
             ms_list = []
             for r in range(a.reps):

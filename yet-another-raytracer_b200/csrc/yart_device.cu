@@ -1137,9 +1137,9 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
   const int chunk_env = tune_env("YART_TUNE_HOST_CHUNK", 1 << 19); // (rays per chunk, read per call; 2^19 measured best: tools/host_chunk_probe.py)
   const uint64_t chunk = dev ? n : (uint64_t)std::max(chunk_env, 1024);
   const uint64_t n_chunks = (n + chunk - 1) / chunk;
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (dev || n_chunks == 1) {
     if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rays.p, rays, n * ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream)); // (stats->gpu_ms: the kernels, not the copies)
     const int rc = run_range(0, n);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1147,14 +1147,15 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
   } else {
     if (!ctx->copy_in) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     if (!ctx->copy_out) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-    while (ctx->chunk_events.size() < 2 * n_chunks + 1) {
+    while (ctx->chunk_events.size() < 3 * n_chunks + 1) {
       cudaEvent_t e;
-      CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreate(&e));
       ctx->chunk_events.push_back(e);
     }
-    cudaEvent_t* up = ctx->chunk_events.data();              // up[i]: chunk i is on the device
-    cudaEvent_t* done = ctx->chunk_events.data() + n_chunks; // done[i]: chunk i's hits are exported
-    cudaEvent_t start = ctx->chunk_events[2 * n_chunks];
+    cudaEvent_t* up = ctx->chunk_events.data();                   // up[i]: chunk i is on the device
+    cudaEvent_t* done = ctx->chunk_events.data() + n_chunks;      // done[i]: chunk i's hits are exported
+    cudaEvent_t* begun = ctx->chunk_events.data() + 2 * n_chunks; // begun[i]: chunk i's kernels start (its upload is in)
+    cudaEvent_t start = ctx->chunk_events[3 * n_chunks];
     // (the device buffers may still be read by earlier work on the context's stream)
     CUDA_TRY(ctx, cudaEventRecord(start, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, start, 0));
@@ -1170,6 +1171,7 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
     for (uint64_t i = 0; i < n_chunks; ++i) {
       const uint64_t off = i * chunk, len = std::min(chunk, n - off);
       CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, up[i], 0));
+      CUDA_TRY(ctx, cudaEventRecord(begun[i], ctx->stream));
       if ((rc = run_range(off, len)) != YART_OK) break;
       CUDA_TRY(ctx, cudaEventRecord(done[i], ctx->stream));
       if (i + 1 < n_chunks && (rc = upload_chunk(i + 1)) != YART_OK) break;
@@ -1192,7 +1194,15 @@ static int closest_hit_impl(yart_ctx* ctx, uint32_t target, const void* rays, bo
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (stats) {
     float ms = 0.f;
-    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (dev || n_chunks == 1) {
+      CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    } else { // the kernels of the chunks, without the waits for their uploads in between
+      for (uint64_t i = 0; i < n_chunks; ++i) {
+        float part = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&part, ctx->chunk_events[2 * n_chunks + i], ctx->chunk_events[n_chunks + i]));
+        ms += part;
+      }
+    }
     stats->rays = n;
     stats->node_visits = c[0];
     stats->tri_tests = c[1];
