@@ -3,15 +3,17 @@
 //
 // k_traverse is bound by the latency of its node / leaf fetches at 16 warps per SM; its 128
 // registers are the price of keeping the f64 ray next to the f32 slab coefficients.  Here everything only the exact
-// f64 code touches -- the ray (o, d), t on entry, the best hit's barycentrics -- lives in shared memory (one column per
+// f64 code touches -- the ray (o, d) and the best hit's barycentrics -- lives in shared memory (one column per
 // lane, conflict-free) and is loaded when a leaf test or a (rare) exact box test needs it, and a leaf's sectors are
-// requested one test ahead instead of all at once.
+// requested one test ahead instead of all at once.  Measured: +7 % on the render step, +6 % on the sweep; at 20 warps
+// the L1 data pipe (82-94 % busy) is the limiter.
 #define YART_TRACE_NO_ANALYTIC_KERNEL
 #include "device_trace.cuh"
 
 namespace yart {
 
-// COMPACT: inner nodes are read from DevMesh::cnodes (64 bytes = TWO sectors per visit instead of four; the kernel is
+// COMPACT (an experiment, off unless YART_TUNE_COMPACT=1; bit-exact but 20-29 % slower -- DESIGN.md section 7):
+// inner nodes are read from DevMesh::cnodes (64 bytes = TWO sectors per visit instead of four; the kernel is
 // bound by L1 data-pipe wavefronts once 20 warps are resident).  The 24 planes of a node are 16-bit offsets q from the
 // mesh's bounding-box corner G in units of s = 2^e: plane = G + q s.  Per ray and axis the slab value is one FMA,
 //     t = fma(m, A, B),   m = float(2^23 + q) (one PRMT builds it from the 16-bit field),  A = s inv32,
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS) k_traverse_lean(con
   constexpr bool MIXED = true;
   __shared__ uint32_t s_stack[STACK + 1][kTraceThreads];
   // what only the exact f64 code needs lives in shared memory, one column per lane: the ray in the mesh's space
-  // (o, d), the interval's upper end on entry, and the barycentrics of the best hit
+  // (o, d) and the barycentrics of the best hit
   __shared__ double s_ray[6][kTraceThreads];
   __shared__ double s_buv[2][kTraceThreads];
   const int tid = threadIdx.x;
