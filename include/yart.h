@@ -370,6 +370,10 @@ int yart_ctx_set_scene(yart_ctx* ctx, const yart_scene_desc* scene);
  *   (constant media use the Philox stream of pixel=ray index, sample 0, bounce 1).
  * rays/hits: n elements, host pointers unless YART_FLAG_DEVICE_PTRS (device ray arrays must be 16-byte
  * aligned, which every cudaMalloc'ed array is).
+ * Rays with zero, infinite or NaN components are legal input: a mesh target reproduces the reference's
+ * NaN-ignoring min / max and its all-false NaN comparisons exactly, and so do the analytic objects.  The one
+ * unspecified case is a ray with NaN components against a GROUP: the reference's BVHNode culls with NaN
+ * comparisons (bvh.rs:151-215), so its own answer depends on the shape of its tree.
  * Host arrays go through in chunks of 2^19 rays, the upload of one chunk and the download of another overlapping the
  * kernels of a third on separate copy streams; page-locked (cudaHostAlloc / cudaHostRegister) arrays make that fully
  * asynchronous -- 0.92 Grays/s (f64 records) / 2.0 Grays/s (f32 records) end to end on a B200 behind PCIe 5, against
