@@ -168,6 +168,17 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(sm), "source": self.how}
 
 
+def warm_up(step, at_least, seconds=0.3):
+    """`at_least` untimed calls of a (synchronous) step, and as many more as it takes to keep the GPU busy for `seconds`:
+    a 5 ms sweep step after seconds of host-side ray generation starts at idle clocks, and three of them are not
+    enough to get back to the boost clock the timed region is then sampled at."""
+    t0, n = time.perf_counter(), 0
+    while n < at_least or time.perf_counter() - t0 < seconds:
+        step()
+        n += 1
+    return n
+
+
 def profiled_traffic():
     """DRAM bytes per ray per k_traverse launch from the committed ncu --set full capture (a PROFILED CONSTANT: ncu's
     numbers cannot be taken live inside a bench run).  Newest round first."""
@@ -678,8 +689,7 @@ def run_sweep(args):
             for order, oname in ((pkg.ORDER_NEAR, "near"), (pkg.ORDER_REFERENCE, "reference")):
                 stc = ctx.closest_hit_device(d_rays.data_ptr(), hi - lo, d_hits.data_ptr(), 0, 0.0, float("inf"), order,
                                              count_visits=True)
-                for _ in range(W):
-                    ctx.closest_hit_device(d_rays.data_ptr(), hi - lo, d_hits.data_ptr(), 0, 0.0, float("inf"), order)
+                warm_up(lambda: ctx.closest_hit_device(d_rays.data_ptr(), hi - lo, d_hits.data_ptr(), 0, 0.0, float("inf"), order), W)
                 rig.barrier()
                 e0, e1 = rig.event(), rig.event()
                 e0.record(rig.stream)
@@ -703,8 +713,7 @@ def run_sweep(args):
                     r32 = np.empty(hi - lo, dtype=pkg.abi.RAY_F32_DTYPE)
                     r32["origin"], r32["direction"] = rays["origin"][lo:hi], rays["direction"][lo:hi]
                     d_r32 = torch.from_numpy(r32.view(np.uint8).reshape(-1)).cuda()
-                    for _ in range(W):
-                        ctx.closest_hit_f32_device(d_r32.data_ptr(), hi - lo, d_hits.data_ptr(), 0, 0.0, float("inf"), order)
+                    warm_up(lambda: ctx.closest_hit_f32_device(d_r32.data_ptr(), hi - lo, d_hits.data_ptr(), 0, 0.0, float("inf"), order), W)
                     rig.barrier()
                     f0, f1 = rig.event(), rig.event()
                     f0.record(rig.stream)
@@ -726,7 +735,7 @@ def run_sweep(args):
     h_hits = torch.empty((hi - lo) * 40, dtype=torch.uint8).pin_memory()
     rays_np = h_rays.numpy().view(pkg.RAY_DTYPE)
     hits_np = h_hits.numpy().view(pkg.HIT_DTYPE)
-    ctx.closest_hit(rays_np, 0, 0.0, float("inf"), pkg.ORDER_NEAR, hits=hits_np)
+    warm_up(lambda: ctx.closest_hit(rays_np, 0, 0.0, float("inf"), pkg.ORDER_NEAR, hits=hits_np), 1)
     rig.barrier()
     e0, e1 = rig.event(), rig.event()
     e0.record(rig.stream)
@@ -742,7 +751,7 @@ def run_sweep(args):
     r32_np = h_r32.numpy().view(pkg.abi.RAY_F32_DTYPE)
     h32_np = h_h32.numpy().view(pkg.abi.HIT_F32_DTYPE)
     r32_np["origin"], r32_np["direction"] = rays_np["origin"], rays_np["direction"]
-    ctx.closest_hit_f32(r32_np, 0, 0.0, float("inf"), pkg.ORDER_NEAR, hits=h32_np)
+    warm_up(lambda: ctx.closest_hit_f32(r32_np, 0, 0.0, float("inf"), pkg.ORDER_NEAR, hits=h32_np), 1)
     rig.barrier()
     g0, g1 = rig.event(), rig.event()
     g0.record(rig.stream)
