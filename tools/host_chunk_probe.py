@@ -21,10 +21,11 @@ h_r32 = torch.empty(n * 24, dtype=torch.uint8).pin_memory(); r32 = h_r32.numpy()
 r32["origin"], r32["direction"] = o, d
 h_h32 = torch.empty(n * 16, dtype=torch.uint8).pin_memory(); h32 = h_h32.numpy().view(y.abi.HIT_F32_DTYPE)
 pageable = rays.copy()
+pageable_hits = np.empty(n, dtype=y.HIT_DTYPE); pageable_hits[:] = 0  # (touched once: no page faults inside the timed calls)
 for chunk in [int(a) for a in sys.argv[1:]] or [1 << 30, 1 << 22, 1 << 21, 1 << 20, 1 << 19]:
     os.environ["YART_TUNE_HOST_CHUNK"] = str(chunk)
     out = []
-    for fn, args in ((ctx.closest_hit, (rays, hits)), (ctx.closest_hit_f32, (r32, h32)), (ctx.closest_hit, (pageable, None))):
+    for fn, args in ((ctx.closest_hit, (rays, hits)), (ctx.closest_hit_f32, (r32, h32)), (ctx.closest_hit, (pageable, pageable_hits))):
         fn(args[0], 0, 0.0, float("inf"), y.ORDER_NEAR, hits=args[1])
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for _ in range(3): fn(args[0], 0, 0.0, float("inf"), y.ORDER_NEAR, hits=args[1])
