@@ -189,6 +189,9 @@ extern "C" {
                                rays: *mut yart_ray, cap: u64, n_out: *mut u64) -> c_int;
     pub fn yart_measure_fetch_peak(ctx: *mut yart_ctx, table_bytes: u64, fetches_per_thread: u32, mode: u32,
                                    gbytes_per_s: *mut f64) -> c_int;
+    // page-lock a Vec the host owns, so that host-array queries and film copies run at the PCIe rate
+    pub fn yart_host_register(ctx: *mut yart_ctx, ptr: *mut c_void, bytes: u64) -> c_int;
+    pub fn yart_host_unregister(ctx: *mut yart_ctx, ptr: *mut c_void) -> c_int;
     // multi-GPU: sample-range sharding + one in-place NCCL reduce of the f64 film (replaces main.rs:746-760)
     pub fn yart_comm_unique_id(id: *mut u8) -> c_int; // YART_COMM_ID_BYTES bytes
     pub fn yart_comm_init_rank(ctx: *mut yart_ctx, id: *const u8, rank: c_int, n_ranks: c_int, out: *mut *mut yart_comm) -> c_int;

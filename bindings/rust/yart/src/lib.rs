@@ -81,6 +81,25 @@ impl GpuScene {
         Ok(hits)
     }
 
+    /// The batched query on buffers the caller keeps (no allocation, no conversion): page-lock them once with `pin`
+    /// and every call moves them over PCIe at full rate, upload / kernels / download overlapped inside the library.
+    pub fn hit_many_into(&self, rays: &[sys::yart_ray], t_min: f64, t_max: f64, hits: &mut [sys::yart_hit]) -> Result<()> {
+        assert_eq!(rays.len(), hits.len());
+        let rc = unsafe {
+            sys::yart_closest_hit(self.ctx, sys::YART_TARGET_WORLD, rays.as_ptr(), rays.len() as u64, t_min, t_max,
+                                  sys::YART_ORDER_NEAR, 0, hits.as_mut_ptr(), ptr::null_mut())
+        };
+        if rc != 0 { Err(self.ctx_err(rc)) } else { Ok(()) }
+    }
+
+    /// Page-lock a slice in place (`yart_host_register`); the guard unlocks it when dropped.  The slice must not be
+    /// reallocated while the guard lives (it borrows it mutably for that reason).
+    pub fn pin<'a, T>(&'a self, buf: &'a mut [T]) -> Result<Pinned<'a, T>> {
+        let rc = unsafe { sys::yart_host_register(self.ctx, buf.as_mut_ptr() as *mut _, std::mem::size_of_val(buf) as u64) };
+        if rc != 0 { return Err(self.ctx_err(rc)); }
+        Ok(Pinned { scene: self, buf })
+    }
+
     /// "" or the sentence a front end must show (a stand-in mesh was loaded for the unshipped bunny.obj / teapot.obj).
     pub fn note(&self) -> String {
         unsafe { CStr::from_ptr(sys::yart_preset_note(self.preset)) }.to_string_lossy().into_owned()
@@ -102,6 +121,18 @@ impl GpuScene {
             if rc != 0 { return Err(self.ctx_err(rc)); }
         }
         Ok(rgba)
+    }
+}
+
+/// A page-locked view of a caller's slice (see `GpuScene::pin`).
+pub struct Pinned<'a, T> {
+    scene: &'a GpuScene,
+    pub buf: &'a mut [T],
+}
+
+impl<'a, T> Drop for Pinned<'a, T> {
+    fn drop(&mut self) {
+        unsafe { sys::yart_host_unregister(self.scene.ctx, self.buf.as_mut_ptr() as *mut _) };
     }
 }
 

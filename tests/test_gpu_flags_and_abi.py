@@ -523,3 +523,28 @@ def test_chunked_host_queries_equal_the_unchunked_ones(yart, ctx, scene, monkeyp
     monkeypatch.setenv("YART_TUNE_HOST_CHUNK", "70001")
     parts32, _ = ctx.closest_hit_f32(r32, yart.TARGET_WORLD, 0.001, INF, yart.ORDER_REFERENCE)
     assert whole32.tobytes() == parts32.tobytes()
+
+
+def test_host_register_pins_caller_arrays(yart, ctx, mesh_scene):
+    """yart_host_register / yart_host_unregister: a host that does not link CUDA page-locks its own arrays."""
+    _, ms, _ = mesh_scene("cube")
+    ctx.set_scene(ms.desc)
+    rng = np.random.default_rng(2)
+    rays = yart.make_rays(rng.uniform(-3, 3, size=(200000, 3)), rng.normal(size=(200000, 3)))
+    hits = np.empty(len(rays), dtype=yart.HIT_DTYPE)
+    want, _ = ctx.closest_hit(rays, 0, 0.001, INF, yart.ORDER_NEAR)
+    ctx.host_register(rays)
+    ctx.host_register(hits)
+    try:
+        got, _ = ctx.closest_hit(rays, 0, 0.001, INF, yart.ORDER_NEAR, hits=hits)
+        assert got.tobytes() == want.tobytes()
+        with pytest.raises(yart.YartError) as e:   # registering the same range twice is refused, not fatal
+            ctx.host_register(rays)
+        assert e.value.code == -1
+    finally:
+        ctx.host_unregister(hits)
+        ctx.host_unregister(rays)
+    with pytest.raises(yart.YartError):            # and so is unlocking what is not locked
+        ctx.host_unregister(rays)
+    got, _ = ctx.closest_hit(rays, 0, 0.001, INF, yart.ORDER_NEAR)  # the context is still usable
+    assert got.tobytes() == want.tobytes()

@@ -22,12 +22,17 @@ r32["origin"], r32["direction"] = o, d
 h_h32 = torch.empty(n * 16, dtype=torch.uint8).pin_memory(); h32 = h_h32.numpy().view(y.abi.HIT_F32_DTYPE)
 pageable = rays.copy()
 pageable_hits = np.empty(n, dtype=y.HIT_DTYPE); pageable_hits[:] = 0  # (touched once: no page faults inside the timed calls)
+registered = rays.copy(); registered_hits = np.zeros(n, dtype=y.HIT_DTYPE)
+import time as _t
+t0 = _t.perf_counter(); ctx.host_register(registered); ctx.host_register(registered_hits)
+print("yart_host_register of %.0f + %.0f MB: %.1f ms" % (registered.nbytes / 1e6, registered_hits.nbytes / 1e6, (_t.perf_counter() - t0) * 1e3), flush=True)
 for chunk in [int(a) for a in sys.argv[1:]] or [1 << 30, 1 << 22, 1 << 21, 1 << 20, 1 << 19]:
     os.environ["YART_TUNE_HOST_CHUNK"] = str(chunk)
     out = []
-    for fn, args in ((ctx.closest_hit, (rays, hits)), (ctx.closest_hit_f32, (r32, h32)), (ctx.closest_hit, (pageable, pageable_hits))):
+    for fn, args in ((ctx.closest_hit, (rays, hits)), (ctx.closest_hit_f32, (r32, h32)), (ctx.closest_hit, (pageable, pageable_hits)),
+                     (ctx.closest_hit, (registered, registered_hits))):
         fn(args[0], 0, 0.0, float("inf"), y.ORDER_NEAR, hits=args[1])
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for _ in range(3): fn(args[0], 0, 0.0, float("inf"), y.ORDER_NEAR, hits=args[1])
         torch.cuda.synchronize(); out.append(3 * n / (time.perf_counter() - t0) / 1e6)
-    print("chunk %10d: f64 pinned %7.1f  f32 pinned %7.1f  f64 pageable %7.1f Mrays/s" % (chunk, *out), flush=True)
+    print("chunk %10d: f64 pinned %7.1f  f32 pinned %7.1f  f64 pageable %7.1f  f64 yart_host_register'ed %7.1f Mrays/s" % (chunk, *out), flush=True)

@@ -68,6 +68,8 @@ def load_library():
         "yart_qbvh_build_device": (i32, [vp, P(abi.Trimesh), P(vp)]),
         "yart_ctx_set_builder": (i32, [vp, u32]),
         "yart_measure_fetch_peak": (i32, [vp, u64, u32, u32, P(f64)]),
+        "yart_host_register": (i32, [vp, vp, u64]),
+        "yart_host_unregister": (i32, [vp, vp]),
         "yart_preset_build": (i32, [C.c_char_p, C.c_char_p, u64, P(vp)]),
         "yart_preset_free": (None, [vp]),
         "yart_preset_note": (C.c_char_p, [vp]),
@@ -120,7 +122,7 @@ EXPORTED_SYMBOLS = [
     "yart_ctx_set_builder", "yart_measure_fetch_peak", "yart_comm_unique_id", "yart_comm_init_rank", "yart_comm_init",
     "yart_comm_destroy", "yart_comm_info", "yart_comm_last_error", "yart_film_reduce", "yart_film_create",
     "yart_film_clear", "yart_film_read", "yart_film_destroy", "yart_preset_note", "yart_closest_hit_f32",
-    "yart_dump_path_rays",
+    "yart_dump_path_rays", "yart_host_register", "yart_host_unregister",
 ]
 
 
@@ -357,6 +359,13 @@ class Context:
         self._check(_lib.yart_closest_hit_f32(self._h, target, C.c_void_p(rays_ptr), n, t_min, t_max, order, flags,
                                               C.c_void_p(hits_ptr), C.byref(st)))
         return st
+
+    def host_register(self, array):
+        """Page-lock a numpy array in place (yart_host_register); pair with host_unregister before the array dies."""
+        self._check(_lib.yart_host_register(self._h, C.c_void_p(array.ctypes.data), array.nbytes))
+
+    def host_unregister(self, array):
+        self._check(_lib.yart_host_unregister(self._h, C.c_void_p(array.ctypes.data)))
 
     def closest_hit_device(self, rays_ptr, n, hits_ptr, target=TARGET_WORLD, t_min=0.001, t_max=float("inf"),
                            order=ORDER_REFERENCE, count_visits=False):

@@ -672,6 +672,39 @@ int yart_ctx_set_stream(yart_ctx* ctx, void* cuda_stream) {
   return YART_OK;
 }
 
+int yart_host_register(yart_ctx* ctx, void* ptr, uint64_t bytes) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!ptr || !bytes) {
+    ctx->err = "yart_host_register: null pointer or zero size";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError(); // not sticky
+    ctx->err = std::string("yart_host_register: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? YART_ERR_NOMEM : YART_ERR_INVALID; // (already registered, not host memory, ...)
+  }
+  return YART_OK;
+}
+
+int yart_host_unregister(yart_ctx* ctx, void* ptr) {
+  if (!ctx) return YART_ERR_INVALID;
+  if (!ptr) {
+    ctx->err = "yart_host_unregister: null pointer";
+    return YART_ERR_INVALID;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // copies from / to the array may still be queued
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ctx->err = std::string("yart_host_unregister: ") + cudaGetErrorString(e);
+    return YART_ERR_INVALID;
+  }
+  return YART_OK;
+}
+
 int yart_ctx_set_builder(yart_ctx* ctx, uint32_t builder) {
   if (!ctx) return YART_ERR_INVALID;
   if (builder > YART_BUILDER_DEVICE) {
