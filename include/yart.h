@@ -463,7 +463,8 @@ int yart_dump_path_rays(yart_ctx* ctx, const yart_camera* camera, const yart_ren
  * fetches `fetches_per_thread` whole 128-byte lines (four 256-bit loads, like one QBVH node visit) at
  * independent random positions of a `table_bytes` table, with the occupancy (20 warps per SM) and cache carveout the
  * traversal kernel runs at (mode 0) or at full occupancy (mode 1).  Returns the sustained rate in GB/s.  A 7 MB table is the david
- * tree: L2-resident, partly L1-resident. */
+ * tree: L2-resident, partly L1-resident.  Modes 2 / 3: the same occupancies, but the four lanes of a quad fetch the four
+ * sectors of ONE line with one 256-bit load each -- the roof of a four-lanes-per-ray traversal. */
 int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetches_per_thread, uint32_t mode,
                             double* gbytes_per_s);
 

@@ -212,6 +212,11 @@ def test_fetch_peak_diagnostic(yart, ctx):
     l1 = ctx.measure_fetch_peak(128 * 1024, 1024, 0)
     l2 = ctx.measure_fetch_peak(7_400_000, 1024, 0)
     assert 1000.0 < l2 < 40000.0 and 1000.0 < l1 < 40000.0 and l1 > 0.9 * l2
+    # modes 2 / 3: four lanes per line (one 256-bit load each) -- far fewer L1 wavefronts per line, a much higher roof
+    quad = ctx.measure_fetch_peak(7_400_000, 1024, 2)
+    assert quad > 1.5 * l2 and ctx.measure_fetch_peak(7_400_000, 1024, 3) > 1.5 * l2
+    with pytest.raises(yart.YartError):
+        ctx.measure_fetch_peak(1 << 20, 1024, 4)
     with pytest.raises(yart.YartError):
         ctx.measure_fetch_peak(64, 1024, 0)
     with pytest.raises(yart.YartError):

@@ -10,4 +10,7 @@ ctx = y.Context(0)
 for mb in (0.125, 0.7, 2, 7.4, 32, 96, 512, 4096):
     a = max(ctx.measure_fetch_peak(int(mb * 1e6), 4096, 0) for _ in range(3))
     b = max(ctx.measure_fetch_peak(int(mb * 1e6), 4096, 1) for _ in range(3))
-    print("table %8.3f MB: %8.0f GB/s at k_traverse's occupancy (16 warps/SM), %8.0f GB/s at full occupancy" % (mb, a, b))
+    c = max(ctx.measure_fetch_peak(int(mb * 1e6), 4096, 2) for _ in range(3))
+    d = max(ctx.measure_fetch_peak(int(mb * 1e6), 4096, 3) for _ in range(3))
+    print("table %8.3f MB: one line per LANE (four loads) %6.0f GB/s at the lean kernel's 20 warps/SM, %6.0f at full occupancy | "
+          "one line per QUAD (one load per lane) %6.0f / %6.0f GB/s" % (mb, a, b, c, d))

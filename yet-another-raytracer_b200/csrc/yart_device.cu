@@ -171,6 +171,24 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_fetch_peak(const float4
   if (acc == 1234.5678f) sink[0] = acc; // keeps the loads alive
 }
 
+// The same with FOUR lanes per line: the lanes of a quad fetch the four 32-byte sectors of ONE random line with a single
+// 256-bit load each (what a 4-lanes-per-ray traversal over child-major nodes would issue per visit).
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_fetch_peak_quad(const float4* __restrict__ table, uint32_t n_lines, uint32_t iters,
+                                                                          float* sink) {
+  const uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+  uint32_t s = (t >> 2) * 2654435761u + 12345u; // (one sequence per quad)
+  float acc = 0.f;
+#pragma unroll 4
+  for (uint32_t i = 0; i < iters; ++i) {
+    s = s * 1664525u + 1013904223u;
+    const uint32_t line = (uint32_t)(((uint64_t)s * n_lines) >> 32);
+    const F8 a = ldg256(table + (size_t)line * 8 + 2 * (t & 3u));
+    acc += a.lo.x + a.hi.w;
+  }
+  if (acc == 1234.5678f) sink[0] = acc;
+}
+
 namespace {
 
 #define CUDA_TRY(ctx, expr)                                                                  \
@@ -1605,7 +1623,7 @@ int yart_generate_camera_rays(yart_ctx* ctx, const yart_camera* cam, const yart_
 int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetches_per_thread, uint32_t mode,
                             double* gbytes_per_s) {
   if (!ctx) return YART_ERR_INVALID;
-  if (!gbytes_per_s || table_bytes < 128 || table_bytes > (1ull << 36) || fetches_per_thread == 0 || mode > 1) {
+  if (!gbytes_per_s || table_bytes < 128 || table_bytes > (1ull << 36) || fetches_per_thread == 0 || mode > 3) {
     ctx->err = "yart_measure_fetch_peak: bad argument";
     return YART_ERR_INVALID;
   }
@@ -1632,8 +1650,11 @@ int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetche
     };
     // mode 0: 128-thread CTAs, 5 per SM -- 20 warps per SM like k_traverse_lean (its register budget, not this
     // kernel's, is what limits it), same carveout; mode 1: whatever fits
+    // modes 2 / 3: the same two occupancies with four lanes per line (k_fetch_peak_quad)
     if (mode == 0) run(k_fetch_peak<128, 5>, 128, true);
-    else run(k_fetch_peak<256, 8>, 256, false);
+    else if (mode == 1) run(k_fetch_peak<256, 8>, 256, false);
+    else if (mode == 2) run(k_fetch_peak_quad<128, 5>, 128, true);
+    else run(k_fetch_peak_quad<256, 8>, 256, false);
     e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   }
@@ -1643,7 +1664,7 @@ int yart_measure_fetch_peak(yart_ctx* ctx, uint64_t table_bytes, uint32_t fetche
     ctx->err = std::string("yart_measure_fetch_peak: ") + cudaGetErrorString(e);
     return YART_ERR_CUDA;
   }
-  *gbytes_per_s = (double)threads * fetches_per_thread * 128.0 / (ms * 1e-3) / 1e9;
+  *gbytes_per_s = (double)threads * fetches_per_thread * (mode >= 2 ? 32.0 : 128.0) / (ms * 1e-3) / 1e9;
   return YART_OK;
 }
 
